@@ -1,0 +1,199 @@
+// Internal declarations shared by the translation units of librsem_b200.so.
+// Nothing here is part of the public ABI (see include/rsem_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rsem_b200.h"
+
+namespace rsem_b200 {
+
+// The reference's clamp constant (utils.h:18): values below it are treated as exactly 0.
+constexpr double kEpsilon = 1e-300;
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define RB_CUDA(call)                                                       \
+    do {                                                                    \
+        cudaError_t _e = (call);                                            \
+        if (_e != cudaSuccess) return ::rsem_b200::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define RB_ARG(cond, msg)                         \
+    do {                                          \
+        if (!(cond)) {                            \
+            ::rsem_b200::set_error(msg);          \
+            return RSEM_B200_ERR_ARG;             \
+        }                                         \
+    } while (0)
+
+// ---- NCCL, loaded at run time (nccl_dyn.cpp) -----------------------------------------------
+struct NcclApi;
+const NcclApi* nccl_api();  // nullptr + last_error set when libnccl.so.2 cannot be loaded
+int nccl_unique_id(void* id128);
+int nccl_comm_init(void** comm, const void* id128, int n_ranks, int rank);
+int nccl_allreduce_sum_f64(void* comm, double* buf, size_t n, cudaStream_t stream);
+int nccl_comm_destroy(void* comm);
+
+// ---- device-side model (pointers into one packed device buffer) -----------------------------
+struct DevLenDist {
+    int lb, ub, span;
+    const double* pdf;
+    const double* cdf;
+};
+
+struct DevModel {
+    int model_type, M, seed_len, est_rspd, rspd_B, has_mld, pro_len;
+    double ori[2];
+    DevLenDist gld, mld;
+    const double* rspd_pdf;
+    const double* rspd_cdf;
+    const double* profile;
+    const double* noise_profile;
+    const double* mw;
+};
+
+// raw accumulation targets of the model-update kernel (K3)
+struct DevStats {
+    double* profile;        // [100|pro_len][5][5]
+    double* noise_profile;  // [100][5] or [5]
+    double* gld_pdf;        // gld_span + 1
+    int gld_lb, gld_span;
+    double* rspd_pdf;       // B + 2
+    size_t total_doubles;   // size of the packed buffer all four point into
+};
+
+struct DevReads {
+    int n_mates = 0;
+    bool has_qual = false;
+    uint64_t* off[2] = {nullptr, nullptr};
+    uint8_t* base[2] = {nullptr, nullptr};
+    uint8_t* qual[2] = {nullptr, nullptr};
+    uint8_t* lowq = nullptr;
+    int max_len = 0;
+};
+
+struct DevRefs {
+    int M = 0;
+    uint64_t* seq_off = nullptr;
+    uint8_t* seq = nullptr;
+    int32_t* full_len = nullptr;
+    int32_t* tot_len = nullptr;
+    uint64_t* mask_off = nullptr;
+    uint32_t* mask_words = nullptr;
+};
+
+struct DevGibbs {
+    uint64_t N1 = 0, E = 0;
+    int M = 0;
+    uint64_t* row_ptr = nullptr;
+    int32_t* sid = nullptr;
+    double* conprb = nullptr;
+};
+
+}  // namespace rsem_b200
+
+struct rsem_b200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    uint64_t dev_bytes = 0;
+
+    // hit matrix
+    uint64_t N = 0, H = 0;
+    int M = 0;
+    uint32_t max_deg = 0;
+    uint64_t* row_ptr = nullptr;
+    int32_t* sid = nullptr;
+    int32_t* pos = nullptr;
+    int32_t* insertL = nullptr;
+    double* conprb = nullptr;
+    double* ncpv = nullptr;
+    double* post = nullptr;   // posterior / frac per hit (lazily allocated)
+    double* post0 = nullptr;  // posterior of the noise entry per read
+    bool conprb_valid = false;
+
+    // E-step tiling (em_kernels.cu)
+    uint64_t* tile_row = nullptr;
+    uint64_t* tile_hit = nullptr;
+    uint32_t n_tiles = 0;
+    int group = 16;       // lanes cooperating on one row
+    int variant = 0;      // 0 auto, 1 TMA-staged, 2 direct
+
+    // EM state
+    double* theta = nullptr;   // M + 1
+    double* count = nullptr;   // M + 1
+    int* done_flag = nullptr;  // device int: 1 once the loop condition ended the run
+    int* err_flag = nullptr;
+    rsem_b200_round_stats* d_stats = nullptr;
+    int stats_cap = 0;
+
+    // model + reads + refs
+    rsem_b200::DevModel model{};
+    double* model_buf = nullptr;
+    size_t model_buf_doubles = 0;
+    bool model_set = false;
+    rsem_b200::DevStats stats{};
+    double* stats_buf = nullptr;
+    size_t stats_buf_doubles = 0;
+    rsem_b200::DevReads reads;
+    rsem_b200::DevRefs refs;
+
+    rsem_b200::DevGibbs gibbs;
+
+    // multi-GPU
+    void* comm = nullptr;
+    int n_ranks = 1, rank = 0;
+
+    // profiling of K2
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+    double estep_ms = 0;
+    uint64_t estep_launches = 0;
+};
+
+namespace rsem_b200 {
+
+// allocation with accounting; every array gets 256 B of tail padding so that 16-byte granular
+// bulk copies may over-read the last tile.
+template <class T>
+int dev_alloc(rsem_b200_ctx* ctx, T** p, size_t n) {
+    size_t bytes = n * sizeof(T) + 256;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    ctx->dev_bytes += bytes;
+    *p = static_cast<T*>(q);
+    return 0;
+}
+template <class T>
+void dev_free(rsem_b200_ctx* ctx, T** p, size_t n) {
+    if (*p) {
+        cudaFree(*p);
+        ctx->dev_bytes -= n * sizeof(T) + 256;
+        *p = nullptr;
+    }
+}
+
+// em_kernels.cu
+int em_build_tiles(rsem_b200_ctx* ctx);
+int em_launch_estep(rsem_b200_ctx* ctx, bool write_post);
+int em_launch_theta_update(rsem_b200_ctx* ctx, double n0, int round, int min_round, int max_round, int stats_slot);
+int em_max_degree(rsem_b200_ctx* ctx, uint32_t* max_deg);
+
+// model_kernels.cu
+int model_launch_conprb(rsem_b200_ctx* ctx);
+int model_launch_update(rsem_b200_ctx* ctx);
+
+// gibbs_kernels.cu
+int gibbs_run(rsem_b200_ctx* ctx, const rsem_b200_gibbs_params* p, rsem_b200_gibbs_out* out);
+
+}  // namespace rsem_b200

@@ -1,0 +1,566 @@
+// E-step / M-step kernels for frozen conditional probabilities (K2) and the theta update +
+// convergence test (K4).
+//
+// What they compute is the reference's E_STEP inner loops (/root/reference/EM.cpp:199-244) and
+// the M-step + relative-change statistics (/root/reference/EM.cpp:385-416).  How they compute
+// it is specific to sm_100a:
+//
+//   * the hit matrix is SoA CSR in HBM (row_ptr u64, sid i32, conprb f64, ncpv f64); one pass
+//     streams 12 B per hit + 16 B per read, nothing else comes from HBM (theta / count live in L2);
+//   * rows are cut into byte-balanced tiles once per upload; a persistent CTA per SM walks its
+//     tiles through a 4-stage shared-memory ring filled by 1-D bulk-async copies (TMA,
+//     cp.async.bulk + mbarrier complete_tx), so the bytes in flight per SM are set by the ring
+//     depth, not by occupancy or by the dependent row_ptr -> hits -> theta load chain;
+//   * a row is reduced by a group of G lanes (G = 4..32, chosen from the mean degree) with
+//     xor-shuffles; normalised weights go to the count vector with red.global.add.f64
+//     (L2-resident), the noise entry count[0] - which every row touches - is privatised in a
+//     register and flushed once per CTA.
+//
+// Clamp semantics are the reference's: a term < 1e-300 is 0, a row whose sum < 1e-300
+// contributes nothing (EM.cpp:212,219,223).
+#include <thrust/device_ptr.h>
+#include <thrust/execution_policy.h>
+#include <thrust/unique.h>
+
+#include "common.cuh"
+
+namespace rsem_b200 {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// tile geometry of the TMA-staged kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kThreads = 512;
+constexpr int kStages = 4;
+constexpr int kTileHitCap = 3072;  // max hits a stage can hold
+constexpr int kTileRowCap = 384;   // max rows a stage can hold
+constexpr int kSidElems = kTileHitCap + 8;
+constexpr int kConElems = kTileHitCap + 4;
+constexpr int kRowElems = kTileRowCap + 4;
+
+struct __align__(16) Stage {
+    double con[kConElems];
+    unsigned long long rp[kRowElems];
+    double ncp[kRowElems];
+    int sid[kSidElems];
+};
+static_assert(sizeof(Stage) % 16 == 0, "stage must keep 16 B alignment");
+
+struct SmemLayout {
+    Stage stage[kStages];
+    unsigned long long full_bar[kStages];
+    double red[kThreads / 32];
+};
+
+struct EstepArgs {
+    const unsigned long long* row_ptr;
+    const int* sid;
+    const double* conprb;
+    const double* ncpv;
+    const double* theta;
+    double* count;
+    double* post;
+    double* post0;
+    const unsigned long long* tile_row;
+    const unsigned long long* tile_hit;
+    unsigned int n_tiles;
+    unsigned long long N;
+    const int* done_flag;
+};
+
+// ---- PTX helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RB_DONE;\n"
+        "bra RB_WAIT;\n"
+        "RB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk asynchronous copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void red_add_f64(double* addr, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ unsigned round16(unsigned bytes) { return (bytes + 15u) & ~15u; }
+
+// One row handled by the G lanes of a group.  sp/cp point at the row's first hit (shared or
+// global memory), `d` is its degree, `g` the lane's index inside the group.
+// Returns the lane's contribution to count[0] (non-zero on g == 0 only).
+template <int G, bool WRITE_POST>
+__device__ __forceinline__ double process_row(bool valid, int g, unsigned d, const int* sp, const double* cp, double nc,
+                                              const double* __restrict__ theta, double theta0, double* count,
+                                              double* post_row, double* post0_row) {
+    double fa = 0.0, fb = 0.0, part = 0.0, f0 = 0.0;
+    int ta = 0, tb = 0;
+    if (valid) {
+        if (g < d) {
+            ta = abs(sp[g]);
+            fa = __ldg(theta + ta) * cp[g];
+            if (fa < kEpsilon) fa = 0.0;
+        }
+        if (g + G < d) {
+            tb = abs(sp[g + G]);
+            fb = __ldg(theta + tb) * cp[g + G];
+            if (fb < kEpsilon) fb = 0.0;
+        }
+        part = fa + fb;
+        for (unsigned j = g + 2 * G; j < d; j += G) {
+            double f = __ldg(theta + abs(sp[j])) * cp[j];
+            if (f < kEpsilon) f = 0.0;
+            part += f;
+        }
+        if (g == 0) {
+            f0 = theta0 * nc;
+            if (f0 < kEpsilon) f0 = 0.0;
+            part += f0;
+        }
+    }
+    const double sum = group_sum<G>(part);
+    double acc0 = 0.0;
+    if (!valid) return 0.0;
+    if (sum >= kEpsilon) {
+        const double inv = 1.0 / sum;
+        if (g == 0) {
+            acc0 = f0 * inv;
+            if (WRITE_POST) *post0_row = acc0;
+        }
+        if (g < d) {
+            const double w = fa * inv;
+            if (fa != 0.0) red_add_f64(count + ta, w);
+            if (WRITE_POST) post_row[g] = w;
+        }
+        if (g + G < d) {
+            const double w = fb * inv;
+            if (fb != 0.0) red_add_f64(count + tb, w);
+            if (WRITE_POST) post_row[g + G] = w;
+        }
+        for (unsigned j = g + 2 * G; j < d; j += G) {
+            const int t = abs(sp[j]);
+            double f = __ldg(theta + t) * cp[j];
+            if (f < kEpsilon) f = 0.0;
+            const double w = f * inv;
+            if (f != 0.0) red_add_f64(count + t, w);
+            if (WRITE_POST) post_row[j] = w;
+        }
+    } else if (WRITE_POST) {
+        if (g == 0) *post0_row = 0.0;
+        for (unsigned j = g; j < d; j += G) post_row[j] = 0.0;
+    }
+    return acc0;
+}
+
+// flush the per-thread count[0] partials: warp shuffle -> shared -> one red per CTA
+__device__ __forceinline__ void flush_count0(double acc0, double* red_smem, double* count) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) red_smem[warp] = acc0;
+    __syncthreads();
+    if (warp == 0) {
+        double v = lane < (blockDim.x >> 5) ? red_smem[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v != 0.0) red_add_f64(count, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2, TMA-staged.  grid = #SMs (persistent), block = kThreads.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage& st, unsigned long long* bar) {
+    const unsigned long long rs = a.tile_row[k], re = a.tile_row[k + 1];
+    const unsigned long long hs = a.tile_hit[k], he = a.tile_hit[k + 1];
+    const unsigned long long hs4 = hs & ~3ull, hs2 = hs & ~1ull, rs2 = rs & ~1ull;
+    const unsigned b_sid = round16((unsigned)(he - hs4) * 4u);
+    const unsigned b_con = round16((unsigned)(he - hs2) * 8u);
+    const unsigned b_rp = round16((unsigned)(re + 1 - rs2) * 8u);
+    const unsigned b_nc = round16((unsigned)(re - rs2) * 8u);
+    mbar_expect_tx(bar, b_sid + b_con + b_rp + b_nc);
+    if (b_sid) bulk_load(st.sid, a.sid + hs4, b_sid, bar);
+    if (b_con) bulk_load(st.con, a.conprb + hs2, b_con, bar);
+    bulk_load(st.rp, a.row_ptr + rs2, b_rp, bar);
+    bulk_load(st.ncp, a.ncpv + rs2, b_nc, bar);
+}
+
+template <int G, bool WRITE_POST>
+__global__ void __launch_bounds__(kThreads, 1) estep_tma_kernel(const EstepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+    if (*a.done_flag) return;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full_bar[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            const unsigned k = blockIdx.x + s * gridDim.x;
+            if (k < a.n_tiles) issue_tile(a, k, sm.stage[s], &sm.full_bar[s]);
+        }
+    }
+
+    constexpr int kGroupsPerWarp = 32 / G;
+    constexpr int kGroups = kThreads / G;
+    const int lane = tid & 31;
+    const int g = lane % G;
+    const int group_in_warp = lane / G;
+    const int warp_first_group = (tid >> 5) * kGroupsPerWarp;
+    const double theta0 = __ldg(a.theta);
+    double acc0 = 0.0;
+
+    unsigned it = 0;
+    for (unsigned k = blockIdx.x; k < a.n_tiles; k += gridDim.x, ++it) {
+        const int s = it % kStages;
+        const unsigned parity = (it / kStages) & 1u;
+        Stage& st = sm.stage[s];
+        mbar_wait(&sm.full_bar[s], parity);
+
+        const unsigned long long rs = a.tile_row[k], re = a.tile_row[k + 1];
+        const unsigned long long hs = a.tile_hit[k];
+        const unsigned long long hs4 = hs & ~3ull, hs2 = hs & ~1ull, rs2 = rs & ~1ull;
+        const unsigned nr = (unsigned)(re - rs);
+        const unsigned roff = (unsigned)(rs - rs2);
+        for (unsigned base = warp_first_group; base < nr; base += kGroups) {
+            const unsigned i = base + group_in_warp;
+            const bool valid = i < nr;
+            unsigned long long rp0 = 0, rp1 = 0;
+            double nc = 0.0;
+            if (valid) {
+                rp0 = st.rp[roff + i];
+                rp1 = st.rp[roff + i + 1];
+                nc = st.ncp[roff + i];
+            }
+            const unsigned d = (unsigned)(rp1 - rp0);
+            acc0 += process_row<G, WRITE_POST>(valid, g, d, st.sid + (rp0 - hs4), st.con + (rp0 - hs2), nc, a.theta,
+                                               theta0, a.count, WRITE_POST ? a.post + rp0 : nullptr,
+                                               WRITE_POST ? a.post0 + rs + i : nullptr);
+        }
+        __syncthreads();  // every thread is done with stage s
+        if (tid == 0) {
+            const unsigned long long kn = (unsigned long long)k + (unsigned long long)kStages * gridDim.x;
+            if (kn < a.n_tiles) issue_tile(a, (unsigned)kn, st, &sm.full_bar[s]);
+        }
+    }
+    flush_count0(acc0, sm.red, a.count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2, direct variant: same row logic, loads straight from global memory (no staging).  Used as
+// the fallback for rows longer than a stage and as the comparison point in the profiles.
+// ------------------------------------------------------------------------------------------------
+template <int G, bool WRITE_POST>
+__global__ void __launch_bounds__(256) estep_direct_kernel(const EstepArgs a) {
+    __shared__ double red[8];
+    if (*a.done_flag) return;
+    constexpr int kGroupsPerWarp = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int g = lane % G;
+    const int group_in_warp = lane / G;
+    const unsigned long long warps_total = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    const unsigned long long warp_id = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const double theta0 = __ldg(a.theta);
+    double acc0 = 0.0;
+    for (unsigned long long base = warp_id * kGroupsPerWarp; base < a.N; base += warps_total * kGroupsPerWarp) {
+        const unsigned long long i = base + group_in_warp;
+        const bool valid = i < a.N;
+        unsigned long long rp0 = 0, rp1 = 0;
+        double nc = 0.0;
+        if (valid) {
+            rp0 = a.row_ptr[i];
+            rp1 = a.row_ptr[i + 1];
+            nc = a.ncpv[i];
+        }
+        const unsigned d = (unsigned)(rp1 - rp0);
+        acc0 += process_row<G, WRITE_POST>(valid, g, d, a.sid + rp0, a.conprb + rp0, nc, a.theta, theta0, a.count,
+                                           WRITE_POST ? a.post + rp0 : nullptr, WRITE_POST ? a.post0 + i : nullptr);
+    }
+    flush_count0(acc0, red, a.count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile construction: tile k holds the rows r with  row_ptr[r] + C * r  in  [k W, (k + 1) W)
+// => at most W / C + 1 rows and at most W + max_degree hits per tile.
+// ------------------------------------------------------------------------------------------------
+__global__ void tile_bounds_kernel(const unsigned long long* row_ptr, unsigned long long N, unsigned long long W,
+                                   unsigned long long C, unsigned long long n_raw, unsigned long long* tile_row) {
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n_raw) return;
+    if (k == n_raw) {
+        tile_row[k] = N;
+        return;
+    }
+    const unsigned long long target = k * W;
+    unsigned long long lo = 0, hi = N;  // first r in [0, N] with row_ptr[r] + C r >= target
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (row_ptr[mid] + C * mid < target) lo = mid + 1;
+        else hi = mid;
+    }
+    tile_row[k] = lo;
+}
+
+__global__ void gather_u64_kernel(const unsigned long long* src, const unsigned long long* idx, unsigned long long n,
+                                  unsigned long long* out) {
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = src[idx[k]];
+}
+
+__global__ void max_degree_kernel(const unsigned long long* row_ptr, unsigned long long N, unsigned int* out) {
+    unsigned int m = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long d = row_ptr[i + 1] - row_ptr[i];
+        m = max(m, d > 0xffffffffull ? 0xffffffffu : (unsigned)d);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: theta update + convergence statistics (EM.cpp:391-416).  The M-vector is tiny (<= 1.6 MB):
+// one CTA, two passes, block reductions.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) theta_update_kernel(double* count, double* theta, int M1, double n0, int round,
+                                                            int min_round, int max_round,
+                                                            rsem_b200_round_stats* stats_slot, int* done_flag,
+                                                            int* err_flag) {
+    __shared__ double sh_d[32];
+    __shared__ long long sh_l[32];
+    __shared__ double sh_sum;
+    if (*done_flag) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+
+    double s = 0.0;
+    for (int i = tid; i < M1; i += blockDim.x) s += count[i];
+    if (tid == 0) s += n0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sh_d[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        double v = lane < nwarp ? sh_d[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh_sum = v;
+    }
+    __syncthreads();
+    const double sum = sh_sum;
+    if (!(sum >= kEpsilon)) {  // reference: assert(sum >= EPSILON), EM.cpp:397
+        if (tid == 0) { *err_flag = 1; *done_flag = 1; }
+        return;
+    }
+
+    double bmax = 0.0;
+    long long tot = 0;
+    for (int i = tid; i < M1; i += blockDim.x) {
+        const double c = count[i] + (i == 0 ? n0 : 0.0);
+        const double tn = c / sum;
+        const double old = theta[i];
+        if (old >= 1e-7) {
+            const double change = fabs(tn - old) / old;
+            if (change >= 0.001) ++tot;
+            if (bmax < change) bmax = change;
+        }
+        theta[i] = tn;
+        count[i] = 0.0;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+        tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    }
+    __syncthreads();
+    if (lane == 0) { sh_d[warp] = bmax; sh_l[warp] = tot; }
+    __syncthreads();
+    if (warp == 0) {
+        double b = lane < nwarp ? sh_d[lane] : 0.0;
+        long long t = lane < nwarp ? sh_l[lane] : 0;
+        for (int o = 16; o > 0; o >>= 1) {
+            b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+        }
+        if (lane == 0) {
+            stats_slot->sum = sum;
+            stats_slot->bchange = b;
+            stats_slot->totnum = t;
+            // loop continues while ROUND < MIN_ROUND || (totNum > 0 && ROUND < MAX_ROUND)
+            if (!(round < min_round || (t > 0 && round < max_round))) *done_flag = 1;
+        }
+    }
+}
+
+template <int G, bool WP>
+int launch_variant(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
+    if (tma) {
+        static bool attr_set = false;
+        auto kern = estep_tma_kernel<G, WP>;
+        const size_t smem = sizeof(SmemLayout);
+        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        (void)attr_set;
+        unsigned grid = ctx->sm_count;
+        if (grid > a.n_tiles) grid = a.n_tiles ? a.n_tiles : 1;
+        kern<<<grid, kThreads, smem, ctx->stream>>>(a);
+    } else {
+        auto kern = estep_direct_kernel<G, WP>;
+        unsigned long long rows_per_block = (256 / 32) * (32 / G);
+        unsigned long long want = (a.N + rows_per_block - 1) / rows_per_block;
+        unsigned grid = (unsigned)std::min<unsigned long long>(want ? want : 1, (unsigned long long)ctx->sm_count * 8);
+        kern<<<grid, 256, 0, ctx->stream>>>(a);
+    }
+    RB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+template <bool WP>
+int launch_group(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
+    switch (ctx->group) {
+        case 4: return launch_variant<4, WP>(ctx, a, tma);
+        case 8: return launch_variant<8, WP>(ctx, a, tma);
+        case 16: return launch_variant<16, WP>(ctx, a, tma);
+        default: return launch_variant<32, WP>(ctx, a, tma);
+    }
+}
+
+}  // namespace
+
+int em_max_degree(rsem_b200_ctx* ctx, uint32_t* max_deg) {
+    unsigned int* d = nullptr;
+    RB_CUDA(cudaMalloc(&d, sizeof(unsigned int)));
+    RB_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned int), ctx->stream));
+    if (ctx->N > 0) {
+        max_degree_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(
+            reinterpret_cast<const unsigned long long*>(ctx->row_ptr), ctx->N, d);
+        ctx->launches++;
+    }
+    RB_CUDA(cudaMemcpyAsync(max_deg, d, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return 0;
+}
+
+int em_build_tiles(rsem_b200_ctx* ctx) {
+    if (ctx->tile_row) { cudaFree(ctx->tile_row); ctx->tile_row = nullptr; }
+    if (ctx->tile_hit) { cudaFree(ctx->tile_hit); ctx->tile_hit = nullptr; }
+    ctx->n_tiles = 0;
+    if (ctx->N == 0) return 0;
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (int rc = em_max_degree(ctx, &ctx->max_deg)) return rc;
+
+    // lanes per row from the mean degree (+1 for the noise entry)
+    const double mean_deg = (double)ctx->H / (double)ctx->N + 1.0;
+    ctx->group = mean_deg <= 5.0 ? 4 : mean_deg <= 11.0 ? 8 : mean_deg <= 26.0 ? 16 : 32;
+
+    if (ctx->max_deg > (uint32_t)kTileHitCap / 2) return 0;  // rows too long for a stage: direct kernel only
+    const unsigned long long W = kTileHitCap - ctx->max_deg;
+    const unsigned long long C = (W + kTileRowCap - 2) / (kTileRowCap - 1);
+    const unsigned long long total = ctx->H + C * ctx->N;
+    const unsigned long long n_raw = total / W + 1;
+    unsigned long long* raw = nullptr;
+    RB_CUDA(cudaMalloc(&raw, (n_raw + 1) * sizeof(unsigned long long)));
+    tile_bounds_kernel<<<(unsigned)((n_raw + 1 + 255) / 256), 256, 0, ctx->stream>>>(
+        reinterpret_cast<const unsigned long long*>(ctx->row_ptr), ctx->N, W, C, n_raw, raw);
+    RB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    // drop empty tiles: consecutive equal boundaries
+    thrust::device_ptr<unsigned long long> p(raw);
+    auto end = thrust::unique(thrust::cuda::par.on(ctx->stream), p, p + n_raw + 1);
+    const unsigned long long n_bounds = (unsigned long long)(end - p);
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_bounds < 2) { cudaFree(raw); return 0; }
+    ctx->n_tiles = (uint32_t)(n_bounds - 1);
+    RB_CUDA(cudaMalloc(&ctx->tile_row, n_bounds * sizeof(uint64_t)));
+    RB_CUDA(cudaMalloc(&ctx->tile_hit, n_bounds * sizeof(uint64_t)));
+    RB_CUDA(cudaMemcpyAsync(ctx->tile_row, raw, n_bounds * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    gather_u64_kernel<<<(unsigned)((n_bounds + 255) / 256), 256, 0, ctx->stream>>>(
+        reinterpret_cast<const unsigned long long*>(ctx->row_ptr),
+        reinterpret_cast<const unsigned long long*>(ctx->tile_row), n_bounds,
+        reinterpret_cast<unsigned long long*>(ctx->tile_hit));
+    RB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(raw);
+    return 0;
+}
+
+int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
+    EstepArgs a;
+    a.row_ptr = reinterpret_cast<const unsigned long long*>(ctx->row_ptr);
+    a.sid = ctx->sid;
+    a.conprb = ctx->conprb;
+    a.ncpv = ctx->ncpv;
+    a.theta = ctx->theta;
+    a.count = ctx->count;
+    a.post = ctx->post;
+    a.post0 = ctx->post0;
+    a.tile_row = reinterpret_cast<const unsigned long long*>(ctx->tile_row);
+    a.tile_hit = reinterpret_cast<const unsigned long long*>(ctx->tile_hit);
+    a.n_tiles = ctx->n_tiles;
+    a.N = ctx->N;
+    a.done_flag = ctx->done_flag;
+    if (ctx->N == 0) return 0;
+    bool tma = ctx->n_tiles > 0 && ctx->variant != 2;
+    if (ctx->variant == 1 && ctx->n_tiles == 0) {
+        set_error("TMA-staged E-step requested but rows are too long for a stage");
+        return RSEM_B200_ERR_UNSUPPORTED;
+    }
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->profiling) {
+        if (ctx->ev_used == ctx->ev_pool.size()) {
+            cudaEvent_t x, y;
+            RB_CUDA(cudaEventCreate(&x));
+            RB_CUDA(cudaEventCreate(&y));
+            ctx->ev_pool.emplace_back(x, y);
+        }
+        e0 = ctx->ev_pool[ctx->ev_used].first;
+        e1 = ctx->ev_pool[ctx->ev_used].second;
+        ctx->ev_used++;
+        RB_CUDA(cudaEventRecord(e0, ctx->stream));
+    }
+    int rc = write_post ? launch_group<true>(ctx, a, tma) : launch_group<false>(ctx, a, tma);
+    if (rc) return rc;
+    if (ctx->profiling) RB_CUDA(cudaEventRecord(e1, ctx->stream));
+    return 0;
+}
+
+int em_launch_theta_update(rsem_b200_ctx* ctx, double n0, int round, int min_round, int max_round, int stats_slot) {
+    theta_update_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->count, ctx->theta, ctx->M + 1, n0, round, min_round,
+                                                     max_round, ctx->d_stats + stats_slot, ctx->done_flag,
+                                                     ctx->err_flag);
+    RB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+}  // namespace rsem_b200

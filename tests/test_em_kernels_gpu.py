@@ -1,0 +1,109 @@
+"""K2 (E-step + count accumulation) and K4 (theta update / convergence) against the CPU oracle.
+
+Tolerance: the path is fp64 with an unordered (atomic) accumulation, the reference itself is only
+reproducible to ~1e-13 across thread counts (-ffast-math); north_star asks for 1e-6 relative on
+theta.  We assert 1e-9 relative on theta >= 1e-7 (the reference's significance floor, EM.cpp:409)
+and 1e-15 absolute below it.
+"""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-9, 1e-15
+
+
+def _check_theta(a, b):
+    big = b >= 1e-7
+    assert np.all(np.abs(a[big] - b[big]) <= RTOL * b[big])
+    assert np.all(np.abs(a[~big] - b[~big]) <= ATOL + RTOL * b[~big])
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    import rsem_b200
+    c = rsem_b200.Context(0)
+    yield c
+    c.close()
+
+
+CASES = [
+    # N, M, avg_deg, zipf, family, zero_rows
+    (1, 5, 3, False, True, 0.0),
+    (37, 50, 1, False, True, 0.0),
+    (5000, 300, 5, False, True, 0.0),
+    (20000, 5000, 10, False, True, 0.0),
+    (20000, 5000, 20, False, False, 0.0),
+    (30000, 2000, 6, True, True, 0.0),
+    (30000, 2000, 40, False, True, 0.0),
+    (4000, 400, 3, False, True, 0.3),
+]
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("case", CASES)
+def test_em_rounds_match_oracle(ctx, oracle, case, variant):
+    N, M, deg, zipf, family, zero_rows = case
+    row_ptr, sid, conprb, ncpv = synth.random_matrix(N, M, deg, seed=N + M, zipf=zipf, family=family, zero_rows=zero_rows)
+    n0 = N / 20
+    theta0 = synth.init_theta(M, n0, N + n0)
+    ctx.set_estep_variant(variant)
+    ctx.upload_hits(row_ptr, sid, M)
+    ctx.upload_conprb(conprb, ncpv)
+    ctx.set_theta(theta0)
+    stats, stopped = ctx.em_rounds(1, 7, 20, 10000, n0)
+    theta_ref, stats_ref, _ = oracle.em_rounds(row_ptr, sid, conprb, ncpv, theta0, n0, 1, 7, 20, 10000)
+    assert len(stats) == 7 and not stopped
+    _check_theta(ctx.get_theta(), theta_ref)
+    for (s, b, t), (s2, b2, t2) in zip(stats, stats_ref):
+        assert abs(s - s2) <= 1e-9 * s2
+        assert abs(b - b2) <= 1e-6 * max(b2, 1e-12)
+        assert abs(t - t2) <= 2  # a change sitting exactly on the 1e-3 threshold may flip
+
+
+def test_stop_condition_on_device(ctx, oracle):
+    """the loop condition ROUND < MIN || (totNum > 0 && ROUND < MAX) is evaluated on the device"""
+    row_ptr, sid, conprb, ncpv = synth.random_matrix(3000, 40, 2, seed=5, tiny_frac=0, family=False)
+    n0 = 100.0
+    theta0 = synth.init_theta(40, n0, 3100)
+    ctx.set_estep_variant(0)
+    ctx.upload_hits(row_ptr, sid, 40)
+    ctx.upload_conprb(conprb, ncpv)
+    ctx.set_theta(theta0)
+    stats, stopped = ctx.em_rounds(1, 400, 5, 300, n0)
+    theta_ref, stats_ref, stopped_ref = oracle.em_rounds(row_ptr, sid, conprb, ncpv, theta0, n0, 1, 400, 5, 300)
+    assert stopped and stopped_ref
+    assert len(stats) == len(stats_ref)
+    _check_theta(ctx.get_theta(), theta_ref)
+
+
+def test_expected_weights(ctx, oracle):
+    row_ptr, sid, conprb, ncpv = synth.random_matrix(8000, 700, 8, seed=9)
+    theta = np.random.default_rng(1).random(701)
+    theta /= theta.sum()
+    for variant in (1, 2):
+        ctx.set_estep_variant(variant)
+        ctx.upload_hits(row_ptr, sid, 700)
+        ctx.upload_conprb(conprb, ncpv)
+        ctx.set_theta(theta)
+        counts = ctx.expected_weights()
+        post, post0 = ctx.download_conprb()
+        c_ref, p_ref, p0_ref = oracle.estep(row_ptr, sid, conprb, ncpv, theta, want_post=True)
+        assert np.allclose(counts, c_ref, rtol=1e-10, atol=1e-13)
+        assert np.allclose(post, p_ref, rtol=1e-12, atol=0)
+        assert np.allclose(post0, p0_ref, rtol=1e-12, atol=0)
+
+
+def test_all_rows_below_epsilon(ctx):
+    """rows whose sum < 1e-300 contribute nothing (EM.cpp:223); with N0 > 0 theta collapses to noise"""
+    row_ptr = np.array([0, 2, 3], np.uint64)
+    sid = np.array([1, -2, 2], np.int32)
+    ctx.set_estep_variant(0)
+    ctx.upload_hits(row_ptr, sid, 2)
+    ctx.upload_conprb(np.array([1e-310, 0.0, 1e-305]), np.array([0.0, 1e-320]))
+    ctx.set_theta(np.array([0.2, 0.4, 0.4]))
+    stats, _ = ctx.em_rounds(1, 1, 20, 100, 3.0)
+    assert stats[0][0] == 3.0
+    assert np.array_equal(ctx.get_theta(), np.array([1.0, 0.0, 0.0]))
