@@ -115,7 +115,11 @@ int check_err_flag(rsem_b200_ctx* ctx) {
     RB_CUDA(cudaMemcpyAsync(&e, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (e) {
-        set_error("sum of expected counts < 1e-300 (reference: assert(sum >= EPSILON), EM.cpp:397)");
+        RB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+        set_error(e == 2 ? "an alignment lies outside its transcript (the reference aborts here: general_assert in "
+                           "getConPrb, e.g. SingleQModel.h:116-121); the aligner may have reported different read "
+                           "lengths for the same read"
+                         : "sum of expected counts < 1e-300 (reference: assert(sum >= EPSILON), EM.cpp:397)");
         return RSEM_B200_ERR_ARG;
     }
     return 0;
@@ -410,7 +414,7 @@ int rsem_b200_calc_conprb(rsem_b200_ctx* c) {
     RB_ARG(((c->model.model_type & 1) != 0) == c->reads.has_qual, "model type does not match quality availability");
     RB_CUDA(cudaSetDevice(c->device));
     if (int rc = model_launch_conprb(c)) return rc;
-    RB_CUDA(cudaStreamSynchronize(c->stream));
+    if (int rc = check_err_flag(c)) return rc;
     c->conprb_valid = true;
     return 0;
 }

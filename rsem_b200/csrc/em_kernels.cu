@@ -22,6 +22,9 @@
 #include <thrust/execution_policy.h>
 #include <thrust/unique.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rsem_b200 {
@@ -213,6 +216,55 @@ __device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage
     bulk_load(st.ncp, a.ncpv + rs2, b_nc, bar);
 }
 
+// Phase B of the staged kernel: one row, reduced by the G lanes of a group, reading the products
+// f = theta[sid] * conprb that phase A left in shared memory (already clamped).
+template <int G, bool WRITE_POST>
+__device__ __forceinline__ double reduce_row(bool valid, int g, unsigned d, const int* sp, const double* fp, double nc,
+                                             double theta0, double* count, double* post_row, double* post0_row) {
+    double fa = 0.0, fb = 0.0, part = 0.0, f0 = 0.0;
+    if (valid) {
+        if (g < d) fa = fp[g];
+        if (g + G < d) fb = fp[g + G];
+        part = fa + fb;
+        for (unsigned j = g + 2 * G; j < d; j += G) part += fp[j];
+        if (g == 0) {
+            f0 = theta0 * nc;
+            if (f0 < kEpsilon) f0 = 0.0;
+            part += f0;
+        }
+    }
+    const double sum = group_sum<G>(part);
+    if (!valid) return 0.0;
+    double acc0 = 0.0;
+    if (sum >= kEpsilon) {
+        const double inv = 1.0 / sum;
+        if (g == 0) {
+            acc0 = f0 * inv;
+            if (WRITE_POST) *post0_row = acc0;
+        }
+        if (g < d) {
+            const double w = fa * inv;
+            if (fa != 0.0) red_add_f64(count + abs(sp[g]), w);
+            if (WRITE_POST) post_row[g] = w;
+        }
+        if (g + G < d) {
+            const double w = fb * inv;
+            if (fb != 0.0) red_add_f64(count + abs(sp[g + G]), w);
+            if (WRITE_POST) post_row[g + G] = w;
+        }
+        for (unsigned j = g + 2 * G; j < d; j += G) {
+            const double f = fp[j];
+            const double w = f * inv;
+            if (f != 0.0) red_add_f64(count + abs(sp[j]), w);
+            if (WRITE_POST) post_row[j] = w;
+        }
+    } else if (WRITE_POST) {
+        if (g == 0) *post0_row = 0.0;
+        for (unsigned j = g; j < d; j += G) post_row[j] = 0.0;
+    }
+    return acc0;
+}
+
 template <int G, bool WRITE_POST>
 __global__ void __launch_bounds__(kThreads, 1) estep_tma_kernel(const EstepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -233,11 +285,11 @@ __global__ void __launch_bounds__(kThreads, 1) estep_tma_kernel(const EstepArgs 
     }
 
     constexpr int kGroupsPerWarp = 32 / G;
-    constexpr int kGroups = kThreads / G;
-    const int lane = tid & 31;
+    constexpr int kWarps = kThreads / 32;
+    constexpr int kUnroll = 4;
+    const int lane = tid & 31, warp = tid >> 5;
     const int g = lane % G;
     const int group_in_warp = lane / G;
-    const int warp_first_group = (tid >> 5) * kGroupsPerWarp;
     const double theta0 = __ldg(a.theta);
     double acc0 = 0.0;
 
@@ -250,25 +302,59 @@ __global__ void __launch_bounds__(kThreads, 1) estep_tma_kernel(const EstepArgs 
 
         const unsigned long long rs = a.tile_row[k], re = a.tile_row[k + 1];
         const unsigned long long hs = a.tile_hit[k];
-        const unsigned long long hs4 = hs & ~3ull, hs2 = hs & ~1ull, rs2 = rs & ~1ull;
         const unsigned nr = (unsigned)(re - rs);
-        const unsigned roff = (unsigned)(rs - rs2);
-        for (unsigned base = warp_first_group; base < nr; base += kGroups) {
-            const unsigned i = base + group_in_warp;
-            const bool valid = i < nr;
-            unsigned long long rp0 = 0, rp1 = 0;
-            double nc = 0.0;
-            if (valid) {
-                rp0 = st.rp[roff + i];
-                rp1 = st.rp[roff + i + 1];
-                nc = st.ncp[roff + i];
+        const unsigned roff = (unsigned)(rs & 1ull);
+        int* s_sid = st.sid + (unsigned)(hs & 3ull);      // element 0 = first hit of the tile
+        double* s_con = st.con + (unsigned)(hs & 1ull);
+        // this warp's contiguous share of the tile's rows (and therefore of its hits)
+        const unsigned r0 = (nr * (unsigned)warp) / kWarps, r1 = (nr * (unsigned)(warp + 1)) / kWarps;
+        if (r1 > r0) {
+            const unsigned h0 = (unsigned)(st.rp[roff + r0] - hs), h1 = (unsigned)(st.rp[roff + r1] - hs);
+            // phase A: f = theta[|sid|] * conprb for every hit, flat over the hit range (all loads
+            // independent, kUnroll gathers in flight per lane), written over the conprb slot
+            for (unsigned h = h0 + lane; h < h1; h += 32 * kUnroll) {
+                int t[kUnroll];
+                double c[kUnroll], th[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const unsigned j = h + 32 * u;
+                    t[u] = j < h1 ? abs(s_sid[j]) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) th[u] = __ldg(a.theta + t[u]);
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const unsigned j = h + 32 * u;
+                    c[u] = j < h1 ? s_con[j] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const unsigned j = h + 32 * u;
+                    double f = th[u] * c[u];
+                    if (f < kEpsilon) f = 0.0;
+                    if (j < h1) s_con[j] = f;
+                }
             }
-            const unsigned d = (unsigned)(rp1 - rp0);
-            acc0 += process_row<G, WRITE_POST>(valid, g, d, st.sid + (rp0 - hs4), st.con + (rp0 - hs2), nc, a.theta,
-                                               theta0, a.count, WRITE_POST ? a.post + rp0 : nullptr,
-                                               WRITE_POST ? a.post0 + rs + i : nullptr);
+            __syncwarp();
+            // phase B: row sums by lane groups, normalised weights to the count vector
+            for (unsigned base = r0; base < r1; base += kGroupsPerWarp) {
+                const unsigned i = base + group_in_warp;
+                const bool valid = i < r1;
+                unsigned long long rp0 = hs, rp1 = hs;
+                double nc = 0.0;
+                if (valid) {
+                    rp0 = st.rp[roff + i];
+                    rp1 = st.rp[roff + i + 1];
+                    nc = st.ncp[roff + i];
+                }
+                const unsigned d = (unsigned)(rp1 - rp0), off = (unsigned)(rp0 - hs);
+                acc0 += reduce_row<G, WRITE_POST>(valid, g, d, s_sid + off, s_con + off, nc, theta0, a.count,
+                                                  WRITE_POST ? a.post + rp0 : nullptr,
+                                                  WRITE_POST ? a.post0 + rs + i : nullptr);
+            }
         }
-        __syncthreads();  // every thread is done with stage s
+        fence_proxy_async();  // generic-proxy writes to the stage precede its next bulk-async fill
+        __syncthreads();      // every thread is done with stage s
         if (tid == 0) {
             const unsigned long long kn = (unsigned long long)k + (unsigned long long)kStages * gridDim.x;
             if (kn < a.n_tiles) issue_tile(a, (unsigned)kn, st, &sm.full_bar[s]);
@@ -480,6 +566,10 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
     // lanes per row from the mean degree (+1 for the noise entry)
     const double mean_deg = (double)ctx->H / (double)ctx->N + 1.0;
     ctx->group = mean_deg <= 5.0 ? 4 : mean_deg <= 11.0 ? 8 : mean_deg <= 26.0 ? 16 : 32;
+    if (const char* e = getenv("RSEM_B200_GROUP")) {  // tuning knob (profiling only)
+        const int v = atoi(e);
+        if (v == 4 || v == 8 || v == 16 || v == 32) ctx->group = v;
+    }
 
     if (ctx->max_deg > (uint32_t)kTileHitCap / 2) return 0;  // rows too long for a stage: direct kernel only
     const unsigned long long W = kTileHitCap - ctx->max_deg;

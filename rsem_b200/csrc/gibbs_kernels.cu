@@ -1,4 +1,332 @@
+// K5 / K6: collapsed Gibbs sampler over read -> transcript assignments (rsem-run-gibbs).
+//
+// Reference: /root/reference/Gibbs.cpp:265-353 (chain), sampling.h:50-65 (categorical draw by
+// binary search on a cumulative array), boost mt19937 + uniform_01 (u = x * 2^-32, one draw per
+// read per sweep).  "Same seed, same draws" is part of the contract, so everything that decides a
+// draw keeps the reference's arithmetic exactly:
+//   * the cumulative array is a LEFT-TO-RIGHT fp64 running sum of (count + alpha) * conprb;
+//   * the drawn index is the number of entries <= u * total, which equals the reference's binary
+//     search because the array is non-decreasing;
+//   * MT19937 is regenerated 624 words at a time by the chain's warp (three dependent phases of the
+//     standard recurrence), tempering is done at extraction.
+//
+// Mapping (round 1): one CTA per chain (chains are the reference's "threads" and never interact),
+// warp 0 walks the reads in order - the loads, the (count + alpha) * conprb products and the
+// index count are spread over its 32 lanes, only the running sum is serial - and the whole CTA
+// does the O(M) per-sample work (count vector dump, theta -> polish -> TPM/FPKM, accumulation).
+// The within-chain dependence (every draw reads counts written by the previous reads) makes this
+// latency-bound; the component-parallel exact scheme of SURVEY.md A.4 is the planned next step.
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
+
 namespace rsem_b200 {
-int gibbs_run(rsem_b200_ctx*, const rsem_b200_gibbs_params*, rsem_b200_gibbs_out*) { set_error("K5 not built yet"); return RSEM_B200_ERR_UNSUPPORTED; }
+namespace {
+
+constexpr int kGibbsThreads = 256;
+constexpr int kRowCap = 2048;  // cumulative-array slots in shared memory; longer rows use global scratch
+
+struct GibbsArgs {
+    unsigned long long N1;
+    const unsigned long long* row_ptr;
+    const int* sid;
+    const double* conprb;
+    int M, burnin, gap, n_genes;
+    const int* chain_samples;
+    const unsigned* chain_seeds;
+    const long long* chain_cv_offset;  // first sample slot of each chain in count_vectors
+    double n0, totc;
+    const int* init_counts;
+    const double* alpha;
+    const double* eel;
+    const double* mw;
+    const int* gene_start;
+    // per-chain state / outputs
+    int* counts;          // n_chains * (M + 1)
+    int* z;               // n_chains * N1
+    double* scratch;      // n_chains * max_len (only when max_len > kRowCap)
+    unsigned max_len;
+    int* count_vectors;   // total_samples * (M + 1)
+    double* acc;          // n_chains * (4 * (M + 1) + n_genes): sum_c, sum_c2, sum_tpm, sum_fpkm, sum_gene_c2
+    double* theta_tmp;    // n_chains * 2 * (M + 1)  (theta / fpkm scratch)
+    int* err_flag;
+};
+
+struct MtState {
+    unsigned mt[624];
+};
+
+__device__ __forceinline__ unsigned mt_twist(unsigned a, unsigned b, unsigned c) {
+    const unsigned y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
+
+// regenerate all 624 words with the 32 lanes of the calling warp
+__device__ void mt_regenerate(MtState& s, int lane) {
+    // phase 1: k in [0, 227) needs old[k], old[k+1], old[k+397]
+    // phase 2: k in [227, 454) needs old[k], old[k+1], new[k-227]
+    // phase 3: k in [454, 623) needs old[k], old[k+1], new[k-227]
+    // phase 4: k = 623 needs old[623], new[0], new[396]
+    const int lo[4] = {0, 227, 454, 623}, hi[4] = {227, 454, 623, 624};
+    for (int p = 0; p < 4; ++p) {
+        unsigned v[8];
+        int n = 0;
+        for (int k = lo[p] + lane; k < hi[p]; k += 32) v[n++] = mt_twist(s.mt[k], s.mt[(k + 1) % 624], s.mt[(k + 397) % 624]);
+        __syncwarp();
+        n = 0;
+        for (int k = lo[p] + lane; k < hi[p]; k += 32) s.mt[k] = v[n++];
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ unsigned mt_temper(unsigned y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+// block-wide sum of doubles (all threads call)
+__device__ double block_sum(double v, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    return t;
+}
+
+// one draw for read i by warp 0 (all 32 lanes call).  use_counts = false for the initial state.
+__device__ __forceinline__ void draw_read(const GibbsArgs& a, unsigned long long i, bool use_counts, int* counts, int* z,
+                                          double* s_arr, double* g_arr, MtState& mt, int& mt_idx, int lane) {
+    const unsigned long long fr = a.row_ptr[i], to = a.row_ptr[i + 1];
+    const unsigned len = (unsigned)(to - fr);
+    double* arr = len <= kRowCap ? s_arr : g_arr;
+    if (use_counts) {
+        if (lane == 0) --counts[z[i]];
+        __syncwarp();
+    }
+    for (unsigned k = lane; k < len; k += 32) {
+        const int t = a.sid[fr + k];
+        const double c = a.conprb[fr + k];
+        arr[k] = use_counts ? ((double)counts[t] + a.alpha[t]) * c : c;
+    }
+    __syncwarp();
+    if (lane == 0) {  // left-to-right running sum (Gibbs.cpp:286-288, 301-308)
+        double run = 0.0;
+        for (unsigned k = 0; k < len; ++k) {
+            run = k ? arr[k] + run : arr[k];
+            arr[k] = run;
+        }
+    }
+    if (mt_idx >= 624) {
+        mt_regenerate(mt, lane);
+        mt_idx = 0;
+    }
+    __syncwarp();
+    const double u = mt_temper(mt.mt[mt_idx]) * (1.0 / 4294967296.0);
+    ++mt_idx;
+    const double prb = u * arr[len - 1];
+    int below = 0;
+    for (unsigned k = lane; k < len; k += 32) below += arr[k] <= prb;
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (below >= (int)len) {  // reference: assert(l < len), sampling.h:62
+        *a.err_flag = 3;
+        below = (int)len - 1;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const int zn = a.sid[fr + below];
+        z[i] = zn;
+        ++counts[zn];
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kGibbsThreads) gibbs_chain_kernel(const GibbsArgs a) {
+    __shared__ MtState mt;
+    __shared__ double s_arr[kRowCap];
+    __shared__ double sh_red[kGibbsThreads / 32];
+    const int chain = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M1 = a.M + 1;
+    int* counts = a.counts + (size_t)chain * M1;
+    int* z = a.z + (size_t)chain * a.N1;
+    double* g_arr = a.scratch ? a.scratch + (size_t)chain * a.max_len : nullptr;
+    double* acc = a.acc + (size_t)chain * (4 * (size_t)M1 + a.n_genes);
+    double* theta = a.theta_tmp + (size_t)chain * 2 * M1;
+    double* fpkm = theta + M1;
+    const int n_samples = a.chain_samples[chain];
+    int* cv = a.count_vectors + a.chain_cv_offset[chain] * M1;
+
+    for (int i = tid; i < M1; i += blockDim.x) counts[i] = a.init_counts[i] + (i == 0 ? (int)a.n0 : 0);
+    if (tid == 0) {  // init_genrand (boost mt19937 seeding)
+        mt.mt[0] = a.chain_seeds[chain];
+        for (int k = 1; k < 624; ++k) mt.mt[k] = 1812433253u * (mt.mt[k - 1] ^ (mt.mt[k - 1] >> 30)) + (unsigned)k;
+    }
+    __syncthreads();
+    int mt_idx = 624;
+
+    if (warp == 0)
+        for (unsigned long long i = 0; i < a.N1; ++i) draw_read(a, i, false, counts, z, s_arr, g_arr, mt, mt_idx, lane);
+    __syncthreads();
+
+    const int chainlen = 1 + (n_samples - 1) * a.gap;
+    int kept = 0;
+    for (int round = 1; round <= a.burnin + chainlen; ++round) {
+        if (warp == 0)
+            for (unsigned long long i = 0; i < a.N1; ++i) draw_read(a, i, true, counts, z, s_arr, g_arr, mt, mt_idx, lane);
+        __syncthreads();
+        if (round > a.burnin && (round - a.burnin - 1) % a.gap == 0) {  // Gibbs.cpp:313-346
+            // count vector + theta = (c + alpha) / totc, zero for omitted; polishTheta; TPM / FPKM
+            double part = 0.0;
+            for (int i = tid; i < M1; i += blockDim.x) {
+                const int c = counts[i];
+                cv[(size_t)kept * M1 + i] = c;
+                double th = c < 0 ? 0.0 : ((double)c + a.alpha[i]) / a.totc;
+                if (i > 0 && (a.mw[i] < kEpsilon || a.eel[i] < kEpsilon)) th = 0.0;
+                else th = th / a.mw[i];
+                theta[i] = th;
+                part += th;
+            }
+            const double tsum = block_sum(part, sh_red);
+            part = 0.0;
+            for (int i = tid; i < M1; i += blockDim.x) {
+                const double th = theta[i] / tsum;
+                theta[i] = th;
+                if (i > 0 && a.eel[i] >= kEpsilon) part += th;
+            }
+            double denom = block_sum(part, sh_red);
+            if (denom < kEpsilon) denom = 1.0;
+            part = 0.0;
+            for (int i = tid; i < M1; i += blockDim.x) {
+                const double f = (i > 0 && a.eel[i] >= kEpsilon) ? (theta[i] / denom) * 1e9 / a.eel[i] : 0.0;
+                fpkm[i] = f;
+                part += f;
+            }
+            double fsum = block_sum(part, sh_red);
+            if (fsum < kEpsilon) fsum = 1.0;
+            for (int i = tid; i < M1; i += blockDim.x) {
+                const double c = (double)counts[i];
+                acc[i] += c;
+                acc[M1 + i] += c * c;
+                acc[2 * (size_t)M1 + i] += i > 0 ? fpkm[i] / fsum * 1e6 : 0.0;
+                acc[3 * (size_t)M1 + i] += fpkm[i];
+            }
+            for (int gi = tid; gi < a.n_genes; gi += blockDim.x) {
+                double c = 0.0;
+                for (int j = a.gene_start[gi]; j < a.gene_start[gi + 1]; ++j) c += counts[j];
+                acc[4 * (size_t)M1 + gi] += c * c;
+            }
+            ++kept;
+            __syncthreads();
+        }
+    }
+}
+
+template <class T>
+int to_dev(T** d, const T* h, size_t n, cudaStream_t s) {
+    RB_CUDA(cudaMalloc(d, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) RB_CUDA(cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+}  // namespace
+
+int gibbs_run(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p, rsem_b200_gibbs_out* out) {
+    const DevGibbs& g = c->gibbs;
+    const int M1 = p->M + 1, nc = p->n_chains;
+    long long total_samples = 0;
+    std::vector<long long> cv_off(nc);
+    for (int t = 0; t < nc; ++t) { cv_off[t] = total_samples; total_samples += p->chain_samples[t]; }
+
+    // longest row decides whether the cumulative array fits shared memory
+    std::vector<uint64_t> h_rp(g.N1 + 1);
+    RB_CUDA(cudaMemcpyAsync(h_rp.data(), g.row_ptr, (g.N1 + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    uint64_t max_len = 1;
+    for (uint64_t i = 0; i < g.N1; ++i) {
+        max_len = std::max(max_len, h_rp[i + 1] - h_rp[i]);
+        if (h_rp[i + 1] == h_rp[i]) { set_error("gibbs: a read without any entry (the .ofg writer never emits one)"); return RSEM_B200_ERR_ARG; }
+    }
+
+    GibbsArgs a{};
+    a.N1 = g.N1;
+    a.row_ptr = reinterpret_cast<const unsigned long long*>(g.row_ptr);
+    a.sid = g.sid;
+    a.conprb = g.conprb;
+    a.M = p->M; a.burnin = p->burnin; a.gap = p->gap; a.n_genes = p->n_genes;
+    a.n0 = p->n0; a.totc = p->totc;
+    a.max_len = (unsigned)max_len;
+    a.err_flag = c->err_flag;
+
+    int *d_samples = nullptr, *d_init = nullptr, *d_gene = nullptr, *d_counts = nullptr, *d_z = nullptr, *d_cv = nullptr;
+    unsigned* d_seeds = nullptr;
+    long long* d_off = nullptr;
+    double *d_alpha = nullptr, *d_eel = nullptr, *d_mw = nullptr, *d_scratch = nullptr, *d_acc = nullptr, *d_tmp = nullptr;
+    const size_t acc_per = 4 * (size_t)M1 + p->n_genes;
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaFree(d_samples); cudaFree(d_init); cudaFree(d_gene); cudaFree(d_counts); cudaFree(d_z); cudaFree(d_cv);
+        cudaFree(d_seeds); cudaFree(d_off); cudaFree(d_alpha); cudaFree(d_eel); cudaFree(d_mw); cudaFree(d_scratch);
+        cudaFree(d_acc); cudaFree(d_tmp);
+    };
+#define RB_TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
+#define RB_TRYC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #x, __FILE__, __LINE__); } } while (0)
+    RB_TRY(to_dev(&d_samples, p->chain_samples, nc, c->stream));
+    RB_TRY(to_dev(&d_seeds, p->chain_seeds, nc, c->stream));
+    RB_TRY(to_dev(&d_off, cv_off.data(), nc, c->stream));
+    RB_TRY(to_dev(&d_init, p->init_counts, M1, c->stream));
+    RB_TRY(to_dev(&d_alpha, p->pseudo_counts, M1, c->stream));
+    RB_TRY(to_dev(&d_eel, p->eel, M1, c->stream));
+    RB_TRY(to_dev(&d_mw, p->mw, M1, c->stream));
+    RB_TRY(to_dev(&d_gene, p->gene_start, (size_t)p->n_genes + 1, c->stream));
+    RB_TRYC(cudaMalloc(&d_counts, (size_t)nc * M1 * sizeof(int)));
+    RB_TRYC(cudaMalloc(&d_z, std::max<size_t>((size_t)nc * g.N1, 1) * sizeof(int)));
+    RB_TRYC(cudaMalloc(&d_cv, std::max<size_t>((size_t)total_samples * M1, 1) * sizeof(int)));
+    RB_TRYC(cudaMalloc(&d_acc, (size_t)nc * acc_per * sizeof(double)));
+    RB_TRYC(cudaMalloc(&d_tmp, (size_t)nc * 2 * M1 * sizeof(double)));
+    RB_TRYC(cudaMemsetAsync(d_acc, 0, (size_t)nc * acc_per * sizeof(double), c->stream));
+    if (max_len > kRowCap) RB_TRYC(cudaMalloc(&d_scratch, (size_t)nc * max_len * sizeof(double)));
+    a.chain_samples = d_samples; a.chain_seeds = d_seeds; a.chain_cv_offset = d_off; a.init_counts = d_init;
+    a.alpha = d_alpha; a.eel = d_eel; a.mw = d_mw; a.gene_start = d_gene; a.counts = d_counts; a.z = d_z;
+    a.scratch = d_scratch; a.count_vectors = d_cv; a.acc = d_acc; a.theta_tmp = d_tmp;
+
+    gibbs_chain_kernel<<<nc, kGibbsThreads, 0, c->stream>>>(a);
+    RB_TRYC(cudaGetLastError());
+    c->launches++;
+
+    std::vector<double> h_acc((size_t)nc * acc_per);
+    RB_TRYC(cudaMemcpyAsync(h_acc.data(), d_acc, h_acc.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RB_TRYC(cudaMemcpyAsync(out->count_vectors, d_cv, (size_t)total_samples * M1 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    int err = 0;
+    RB_TRYC(cudaMemcpyAsync(&err, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    RB_TRYC(cudaStreamSynchronize(c->stream));
+    cleanup();
+#undef RB_TRY
+#undef RB_TRYC
+    if (err) {
+        cudaMemset(c->err_flag, 0, sizeof(int));
+        set_error("gibbs: categorical draw fell off the cumulative array (reference: assert(l < len), sampling.h:62)");
+        return RSEM_B200_ERR_ARG;
+    }
+    // sum the per-chain accumulators in chain order (Gibbs.cpp:372-397)
+    for (int i = 0; i < M1; ++i) out->sum_c[i] = out->sum_c2[i] = out->sum_tpm[i] = out->sum_fpkm[i] = 0.0;
+    for (int gi = 0; gi < p->n_genes; ++gi) out->sum_gene_c2[gi] = 0.0;
+    for (int t = 0; t < nc; ++t) {
+        const double* b = h_acc.data() + (size_t)t * acc_per;
+        for (int i = 0; i < M1; ++i) {
+            out->sum_c[i] += b[i];
+            out->sum_c2[i] += b[M1 + i];
+            out->sum_tpm[i] += b[2 * (size_t)M1 + i];
+            out->sum_fpkm[i] += b[3 * (size_t)M1 + i];
+        }
+        for (int gi = 0; gi < p->n_genes; ++gi) out->sum_gene_c2[gi] += b[4 * (size_t)M1 + gi];
+    }
+    return 0;
+}
+
+}  // namespace rsem_b200

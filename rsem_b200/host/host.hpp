@@ -1,0 +1,160 @@
+// Host side of the drop-in executables rsem-run-em / rsem-run-gibbs.
+//
+// Everything here is O(input) parsing, O(table) model bookkeeping and O(M) output math; all per-hit
+// and per-read arithmetic runs on the GPU through the C ABI (include/rsem_b200.h).
+// File formats and semantics follow the reference (citations per function, paths relative to
+// /root/reference); the code structure does not: one table-oriented HostModel instead of four
+// template classes, SoA read/hit stores instead of streams of objects.
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "rsem_b200.h"
+
+namespace host {
+
+constexpr double kEps = 1e-300;     // utils.h:18 EPSILON
+constexpr double kMinEel = 1.0;     // utils.h:19 MINEEL
+constexpr int kOlen = 25;           // utils.h:23 OLEN
+constexpr int kRange = 201;         // utils.h:22 RANGE
+
+extern bool g_verbose;
+
+[[noreturn]] void die(const std::string& msg);          // message to stderr, exit(-1) (my_assert.h:34-41)
+void check_rc(int rc, const char* what);                // C-ABI error -> die(rsem_b200_last_error())
+
+// ---- reference transcripts: ref.seq (RefSeq.h:108-127), ref.ti (Transcript.h:119-146), ref.grp ----
+struct RefData {
+    int M = 0;
+    bool has_polyA = false;
+    std::vector<uint64_t> seq_off;   // M + 2 (index 0 unused)
+    std::vector<uint8_t> seq;        // base codes, forward strand, totLen per transcript
+    std::vector<int32_t> full_len, tot_len;  // M + 1
+    std::vector<uint64_t> mask_off;  // M + 1
+    std::vector<uint32_t> mask_words;
+    bool mask(int sid, int p) const { return (mask_words[mask_off[sid] + p / 32] >> (p % 32)) & 1u; }
+};
+void load_refs(const std::string& path, bool with_seqs, RefData& out);  // Refs::loadRefs, Refs.h:118-145
+
+struct TranscriptInfo {
+    std::string transcript_id, transcript_name, gene_id, gene_name, seqname;
+    int length = 0;
+};
+void load_transcripts(const std::string& path, std::vector<TranscriptInfo>& out);  // index 1..M
+void load_groups(const std::string& path, std::vector<int>& starts);               // GroupInfo.h:34-53
+bool load_allele_groups(const std::string& ref_name, std::vector<int>& gt, std::vector<int>& ta);  // WriteResults.h:106-123
+
+// ---- reads (SingleRead(Q).h, PairedEndRead(Q).h, ReadReader.h) ------------------------------------
+struct ReadStore {
+    int n_mates = 1;
+    bool has_qual = false;
+    uint64_t n = 0;
+    std::vector<uint64_t> off[2];
+    std::vector<uint8_t> base[2], qual[2];
+    std::vector<uint8_t> lowq;
+};
+// Parses a whole read set (tag 0 "un", 1 "alignable", 2 "max"; utils.h:129-149).  calc_lq as
+// SingleReadQ.h:63-95 / PairedEndReadQ.h:58-65.  `keep` = false only streams statistics through `visit`.
+struct ReadVisitor {
+    virtual ~ReadVisitor() {}
+    // called once per read; b/q point at codes of each mate (q null without qualities)
+    virtual void read(bool lowq, int n_mates, const uint8_t* const b[2], const uint8_t* const q[2], const int len[2],
+                      const std::string& name) = 0;
+};
+void parse_reads(const std::string& imd_name, int tag, int read_type, bool has_polyA, int seed_len, ReadStore* keep,
+                 ReadVisitor* visit);
+
+// ---- hits: imd.dat (HitContainer.h:62-79, parseIt.cpp:197-211) -----------------------------------
+struct HitStore {
+    uint64_t N = 0, H = 0;
+    std::vector<uint64_t> row_ptr;
+    std::vector<int32_t> sid, pos, insertL;
+};
+void load_dat(const std::string& path, int read_type, uint64_t expect_n1, HitStore& out);
+
+// ---- model -------------------------------------------------------------------------------------
+struct LenDistH {  // LenDist.h
+    int lb = 0, ub = 1000, span = 1000;
+    std::vector<double> pdf, cdf;
+    LenDistH() { reset(1, 1000); }
+    void reset(int minL, int maxL);         // constructor LenDist.h:17-32 (uniform)
+    void zero();                            // init()
+    void finish();                          // normalise + cdf + trim (LenDist.h:186-200)
+    void trim();                            // LenDist.h:265-294
+    void set_as_normal(double mean, double sd, int minL, int maxL);  // LenDist.h:91-179
+    double prob(int len) const { return pdf[len - lb]; }
+    double adj(int len, int refL) const;    // getAdjustedProb
+    double adj_cum(int len, int refL) const;  // getAdjustedCumulativeProb
+    int minL() const { return lb + 1; }
+    int maxL() const { return ub; }
+    void write(FILE* fo) const;             // LenDist.h:237-243
+    void read(FILE* fi);                    // LenDist.h:221-235
+};
+
+struct ModelParamsH {  // ModelParams.h + imd.mparams
+    int M = 0;
+    uint64_t N[3] = {0, 0, 0};
+    int minL = 1, maxL = 1000, B = 20, mate_minL = 1, mate_maxL = 1000, seedLen = 0;
+    bool estRSPD = false;
+    double probF = 0.5, mean = -1, sd = 0;
+};
+void load_mparams(const std::string& path, ModelParamsH& p);  // EM.cpp:647-658
+
+struct HostModel {
+    int type = 0;  // 0..3
+    ModelParamsH mp;
+    const RefData* refs = nullptr;
+    double ori[2] = {0.5, 0.5};
+    LenDistH gld, mld;
+    bool has_mld = false;
+    // RSPD (RSPD.h)
+    std::vector<double> rspd_pdf, rspd_cdf;  // B + 2
+    // QualDist (QualDist.h), Q models only
+    std::vector<double> qd_init, qd_tran;
+    // Profile / QProfile
+    int pro_len = 0;
+    std::vector<double> profile;
+    // Noise(Q)Profile: p and the N0 counts c
+    std::vector<double> noise_p, noise_c;
+    std::vector<double> mw;  // M + 1
+
+    bool hasq() const { return type & 1; }
+    bool paired() const { return type >= 2; }
+    size_t n_prof() const { return hasq() ? 2500 : (size_t)pro_len * 25; }
+    size_t n_noise() const { return hasq() ? 500 : 5; }
+
+    void init_master(int model_type, const ModelParamsH& p, const RefData* refs);  // Model(ModelParams&, true)
+    void estimate_from_reads(const std::string& imd_name, ReadStore& alignable);    // estimateFromReads
+    // init(); collect(helpers); finish()  (EM.cpp:400-404) from the device sufficient statistics
+    void rebuild(const rsem_b200_model_stats& st);
+    void calc_mw();
+    double rspd_eval_cdf(int fpos, int fullLen) const;
+    double rspd_adj(int fpos, int effL, int fullLen) const;
+    void fill_abi(rsem_b200_model& m) const;
+    void write(const std::string& path) const;   // Model::write
+    // Model::read for rsem-run-gibbs: only gld and mw are needed afterwards, but the whole file is parsed
+    static void read_for_gibbs(const std::string& path, int M, int& model_type, LenDistH& gld, std::vector<double>& mw);
+};
+
+// ---- O(M) result math (WriteResults.h:24-104) ------------------------------------------------------
+void calc_eel(const RefData& refs, const LenDistH& gld, std::vector<double>& eel);
+void polish_theta(std::vector<double>& theta, const std::vector<double>& eel, const std::vector<double>& mw);
+void expression_values(const std::vector<double>& theta, const std::vector<double>& eel, std::vector<double>& tpm,
+                       std::vector<double>& fpkm);
+void write_results_em(const std::string& ref_name, const std::string& imd_name, const std::vector<TranscriptInfo>& tr,
+                      const std::vector<double>& theta, const std::vector<double>& eel, const double* counts,
+                      bool append_names);  // WriteResults.h:125-355
+void write_results_gibbs(const std::string& ref_name, const std::string& imd_name, int M, const std::vector<double>& pme_c,
+                         const std::vector<double>& pme_fpkm, const std::vector<double>& pme_tpm,
+                         const std::vector<double>& pve_c, const std::vector<double>& pve_c_genes,
+                         const std::vector<double>& pve_c_trans);  // WriteResults.h:357-479
+
+// ---- small utilities -----------------------------------------------------------------------------
+std::vector<char> slurp(const std::string& path, bool must_exist = true);
+void read_type_files(const std::string& imd_name, int tag, int read_type, std::vector<std::string>& files);
+uint32_t parse_seed(const char* s);  // digit-by-digit as EM.cpp:588-593
+
+}  // namespace host

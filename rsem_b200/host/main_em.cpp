@@ -1,0 +1,259 @@
+// rsem-run-em, B200 edition: same argv, same input and output files as the reference executable
+// (/root/reference/EM.cpp:541-675), so it drops in beside the unmodified rsem-calculate-expression.
+//
+//   rsem-run-em refName read_type sampleName imdName statName [-p #Threads] [-b samInpF has_fai? [fai_file]]
+//               [-q] [--gibbs-out] [--sampling] [--seed seed] [--append-names]
+//
+// Differences from the reference, all outside the results:
+//   * -p is accepted and ignored for the EM (the result of the reference does not depend on it);
+//     the GPU is chosen with RSEM_B200_DEVICE (default 0).
+//   * -b (posterior BAM output) is not implemented yet: the run stops with an
+//     error before doing any work, so the Perl driver must be called with --no-bam-output.
+//   * RSEM_MAX_ROUND / RSEM_MIN_ROUND override the compile-time constants MAX_ROUND = 10000 and
+//     MIN_ROUND = 20 (EM.cpp:54-55), like oracle/_ref/rsem-run-em-rounds, for fixed-round parity runs.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+
+#include "host.hpp"
+
+using namespace host;
+
+namespace {
+
+struct Args {
+    std::string refName, outName, imdName, statName;
+    int read_type = 0;
+    bool genBam = false, bamSampling = false, gibbsOut = false, hasSeed = false, appendNames = false;
+    uint32_t seed = 0;
+};
+
+void usage() {
+    printf("Usage : rsem-run-em refName read_type sampleName imdName statName [-p #Threads] [-b samInpF has_fai? [fai_file]] [-q] [--gibbs-out] [--sampling] [--seed seed] [--append-names]\n\n");
+    printf("  refName: reference name\n");
+    printf("  read_type: 0 single read without quality score; 1 single read with quality score; 2 paired-end read without quality score; 3 paired-end read with quality score.\n");
+    printf("  sampleName: sample's name, including the path\n");
+    printf("  sampleToken: sampleName excludes the path\n");
+    printf("  -p: number of threads which user wants to use. (default: 1)\n");
+    printf("  -b: produce bam format output file. (default: off)\n");
+    printf("  -q: set it quiet\n");
+    printf("  --gibbs-out: generate output file used by Gibbs sampler. (default: off)\n");
+    printf("  --sampling: sample each read from its posterior distribution when BAM file is generated. (default: off)\n");
+    printf("  --seed uint32: the seed used for the BAM sampling. (default: off)\n");
+    printf("  --append-names: append transcript_name/gene_name when available. (default: off)\n");
+    printf("// model parameters should be in imdName.mparams.\n");
+    exit(-1);
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+void print_round(int round, const rsem_b200_round_stats& s) {
+    if (g_verbose) printf("ROUND = %d, SUM = %.15g, bChange = %.6g, totNum = %lld\n", round, s.sum, s.bchange, (long long)s.totnum);
+}
+
+// imd.ofg, EM.cpp:435-457: "M N0" then one line per read with >= 1 surviving entry
+void write_ofg(const std::string& path, int M, uint64_t N0, const HitStore& h, const std::vector<double>& conprb,
+               const std::vector<double>& ncpv) {
+    FILE* fo = fopen(path.c_str(), "w");
+    if (!fo) die("Cannot open " + path + " for writing!");
+    static char buf[1 << 20];
+    setvbuf(fo, buf, _IOFBF, sizeof buf);
+    fprintf(fo, "%d %llu\n", M, (unsigned long long)N0);
+    for (uint64_t i = 0; i < h.N; ++i) {
+        int tot = 0;
+        if (ncpv[i] >= kEps) { ++tot; fprintf(fo, "0 %.15g ", ncpv[i]); }
+        for (uint64_t j = h.row_ptr[i]; j < h.row_ptr[i + 1]; ++j)
+            if (conprb[j] >= kEps) { ++tot; fprintf(fo, "%d %.15g ", abs(h.sid[j]), conprb[j]); }
+        if (tot > 0) fputc('\n', fo);
+    }
+    fclose(fo);
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+    if (argc < 6) usage();
+    const time_t t_start = time(NULL);
+    Args a;
+    a.refName = argv[1];
+    a.read_type = atoi(argv[2]);
+    a.outName = argv[3];
+    a.imdName = argv[4];
+    a.statName = argv[5];
+    int nThreads = 1;
+    for (int i = 6; i < argc; ++i) {
+        if (!strcmp(argv[i], "-p") && i + 1 < argc) nThreads = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "-b")) a.genBam = true;
+        if (!strcmp(argv[i], "-q")) g_verbose = false;
+        if (!strcmp(argv[i], "--gibbs-out")) a.gibbsOut = true;
+        if (!strcmp(argv[i], "--sampling")) a.bamSampling = true;
+        if (!strcmp(argv[i], "--seed") && i + 1 < argc) { a.hasSeed = true; a.seed = parse_seed(argv[i + 1]); }
+        if (!strcmp(argv[i], "--append-names")) a.appendNames = true;
+    }
+    if (nThreads <= 0) die("Number of threads should be bigger than 0!");
+    if (a.read_type < 0 || a.read_type > 3) { fprintf(stderr, "Unknown Read Type!\n"); exit(-1); }
+    if (a.genBam)
+        die("rsem-run-em (B200): -b (posterior BAM output) is not implemented; run rsem-calculate-expression with --no-bam-output.");
+
+    RefData refs;
+    load_refs(a.refName + ".seq", true, refs);
+    const int M = refs.M;
+    std::vector<TranscriptInfo> transcripts;
+    load_transcripts(a.refName + ".ti", transcripts);
+
+    uint64_t N0, N1, N2, N_tot;
+    {
+        std::vector<char> b = slurp(a.statName + ".cnt");
+        b.push_back(0);
+        unsigned long long v[4];
+        if (sscanf(b.data(), "%llu %llu %llu %llu", &v[0], &v[1], &v[2], &v[3]) != 4) die("Cannot parse " + a.statName + ".cnt!");
+        N0 = v[0]; N1 = v[1]; N2 = v[2]; N_tot = v[3];
+    }
+
+    std::vector<double> theta(M + 1, 0.0), eel;
+    if (N1 == 0) {  // EM.cpp:615-638
+        printf("Warning: There are no alignable reads!\n");
+        FILE* fo = fopen((a.statName + ".theta").c_str(), "w");
+        if (fo) fclose(fo);
+        fo = fopen((a.statName + ".model").c_str(), "w");
+        if (fo) fclose(fo);
+        eel.assign(M + 1, 0.0);
+        for (int i = 1; i <= M; ++i) eel[i] = transcripts[i].length;
+        std::vector<double> countv(M + 1, 0.0);
+        write_results_em(a.refName, a.imdName, transcripts, theta, eel, countv.data(), a.appendNames);
+        const time_t t_end = time(NULL);
+        printf("Time Used for EM.cpp : %d h %02d m %02d s\n", int((t_end - t_start) / 3600), int((t_end - t_start) % 3600 / 60), int((t_end - t_start) % 60));
+        return 0;
+    }
+
+    ModelParamsH mp;
+    mp.M = M;
+    mp.N[0] = N0; mp.N[1] = N1; mp.N[2] = N2;
+    load_mparams(a.imdName + ".mparams", mp);
+
+    const int MAX_ROUND = env_int("RSEM_MAX_ROUND", 10000), MIN_ROUND = env_int("RSEM_MIN_ROUND", 20);
+
+    // ---- init (EM.cpp:97-174): hits from .dat; the GPU holds the whole read range ----
+    HitStore hits;
+    load_dat(a.imdName + ".dat", a.read_type, N1, hits);
+    if (g_verbose) {
+        printf("Thread 0 : N = %llu, NHit = %llu\n", (unsigned long long)hits.N, (unsigned long long)hits.H);
+        printf("EM_init finished!\n");
+    }
+
+    // initial theta (EM.cpp:342-346)
+    if (!(N_tot > N2)) die("N_tot must be larger than N2!");
+    theta[0] = std::max(N0 * 1.0 / (N_tot - N2), 1e-8);
+    for (int i = 1; i <= M; ++i) theta[i] = (1.0 - theta[0]) / M;
+
+    HostModel model;
+    model.init_master(a.read_type, mp, &refs);
+    ReadStore reads;
+    model.estimate_from_reads(a.imdName, reads);
+    if (reads.n != N1) die("Read indices files do not match!");
+
+    // ---- device set-up ----
+    rsem_b200_ctx* ctx = nullptr;
+    check_rc(rsem_b200_ctx_create(env_int("RSEM_B200_DEVICE", 0), &ctx), "ctx_create");
+    check_rc(rsem_b200_upload_hits(ctx, hits.N, hits.H, M, hits.row_ptr.data(), hits.sid.data(), hits.pos.data(),
+                                   a.read_type >= 2 ? hits.insertL.data() : nullptr), "upload_hits");
+    check_rc(rsem_b200_upload_reads(ctx, reads.n_mates, reads.off[0].data(), reads.base[0].data(),
+                                    reads.has_qual ? reads.qual[0].data() : nullptr,
+                                    reads.n_mates == 2 ? reads.off[1].data() : nullptr,
+                                    reads.n_mates == 2 ? reads.base[1].data() : nullptr,
+                                    (reads.n_mates == 2 && reads.has_qual) ? reads.qual[1].data() : nullptr,
+                                    reads.lowq.data()), "upload_reads");
+    check_rc(rsem_b200_upload_refs(ctx, M, refs.seq_off.data(), refs.seq.data(), refs.full_len.data(), refs.tot_len.data(),
+                                   refs.mask_off.data(), refs.mask_words.data()), "upload_refs");
+    check_rc(rsem_b200_set_theta(ctx, theta.data()), "set_theta");
+
+    // ---- EM loop (EM.cpp:364-416) ----
+    std::vector<double> st_prof(model.n_prof()), st_noise(model.n_noise()), st_gld(mp.maxL - (mp.minL - 1) + 1), st_rspd(mp.B + 2);
+    rsem_b200_model_stats mstats;
+    mstats.profile = st_prof.data();
+    mstats.noise_profile = st_noise.data();
+    mstats.gld_pdf = st_gld.data();
+    mstats.gld_lb = mp.minL - 1;
+    mstats.gld_span = mp.maxL - (mp.minL - 1);
+    mstats.rspd_pdf = st_rspd.data();
+
+    bool model_dirty = true;  // device copy of the model tables / conprb is stale (needCalcConPrb)
+    auto push_model = [&]() {
+        rsem_b200_model abi;
+        model.fill_abi(abi);
+        check_rc(rsem_b200_set_model(ctx, &abi), "set_model");
+    };
+    int ROUND = 0;
+    long long totNum = 0;
+    const int CHUNK = 32;
+    std::vector<rsem_b200_round_stats> chunk_stats(CHUNK);
+    bool keep_going = true;
+    while (keep_going) {
+        ++ROUND;
+        if (ROUND <= 10) {  // doesUpdateModel, EM.cpp:307-310
+            if (model_dirty) { push_model(); model_dirty = false; }
+            rsem_b200_round_stats rs;
+            check_rc(rsem_b200_em_model_round(ctx, (double)N0, &mstats, &rs), "em_model_round");
+            model.rebuild(mstats);  // model.init(); collect(); finish()
+            model_dirty = true;
+            print_round(ROUND, rs);
+            totNum = rs.totnum;
+            keep_going = ROUND < MIN_ROUND || (totNum > 0 && ROUND < MAX_ROUND);
+        } else {
+            if (model_dirty) {
+                push_model();
+                check_rc(rsem_b200_calc_conprb(ctx), "calc_conprb");
+                model_dirty = false;
+            }
+            int32_t ran = 0, stopped = 0;
+            check_rc(rsem_b200_em_rounds(ctx, ROUND, CHUNK, MIN_ROUND, MAX_ROUND, (double)N0, chunk_stats.data(), &ran, &stopped), "em_rounds");
+            for (int r = 0; r < ran; ++r) print_round(ROUND + r, chunk_stats[r]);
+            if (ran > 0) { ROUND += ran - 1; totNum = chunk_stats[ran - 1].totnum; }
+            keep_going = !stopped;
+        }
+    }
+    if (totNum > 0) fprintf(stderr, "Warning: RSEM reaches %d iterations before meeting the convergence criteria.\n", MAX_ROUND);
+
+    // ---- .ofg (EM.cpp:421-457) ----
+    if (model_dirty) {  // calcConProbs when the loop ended inside the model rounds
+        push_model();
+        check_rc(rsem_b200_calc_conprb(ctx), "calc_conprb");
+        model_dirty = false;
+    }
+    std::vector<double> conprb(hits.H), ncpv(hits.N);
+    if (a.gibbsOut) {
+        check_rc(rsem_b200_download_conprb(ctx, conprb.data(), ncpv.data()), "download_conprb");
+        write_ofg(a.imdName + ".ofg", M, N0, hits, conprb, ncpv);
+    }
+
+    // ---- expected weights with the learned parameters (EM.cpp:460-478) ----
+    check_rc(rsem_b200_get_theta(ctx, theta.data()), "get_theta");
+    std::vector<double> counts(M + 1, 0.0);
+    check_rc(rsem_b200_expected_weights(ctx, counts.data()), "expected_weights");
+    counts[0] += N0;
+
+    // ---- .theta (EM.cpp:484-500) ----
+    FILE* fo = fopen((a.statName + ".theta").c_str(), "w");
+    if (!fo) die("Cannot open " + a.statName + ".theta for writing!");
+    fprintf(fo, "%d\n", M + 1);
+    for (int i = 0; i < M; ++i) fprintf(fo, "%.15g ", theta[i]);
+    fprintf(fo, "%.15g\n", theta[M]);
+    calc_eel(refs, model.gld, eel);
+    polish_theta(theta, eel, model.mw);
+    for (int i = 0; i < M; ++i) fprintf(fo, "%.15g ", theta[i]);
+    fprintf(fo, "%.15g\n", theta[M]);
+    fclose(fo);
+
+    model.write(a.statName + ".model");
+    write_results_em(a.refName, a.imdName, transcripts, theta, eel, counts.data(), a.appendNames);
+
+    rsem_b200_ctx_destroy(ctx);
+    const time_t t_end = time(NULL);
+    printf("Time Used for EM.cpp : %d h %02d m %02d s\n", int((t_end - t_start) / 3600), int((t_end - t_start) % 3600 / 60), int((t_end - t_start) % 60));
+    return 0;
+}

@@ -1,0 +1,278 @@
+// rsem-run-gibbs, B200 edition: same argv and files as the reference (/root/reference/Gibbs.cpp:425-530).
+//
+//   rsem-run-gibbs reference_name imdName statName BURNIN NSAMPLES GAP [-p #Threads] [--seed seed]
+//                  [--pseudo-count pseudo_count] [--prior file] [-q]
+//
+// -p keeps its meaning: it is the number of independent chains (the results depend on it, exactly as in
+// the reference: NSAMPLES is split over the chains and each chain gets its own mt19937 seed).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <set>
+
+#include "host.hpp"
+
+using namespace host;
+
+namespace {
+
+// minimal host MT19937, only to derive the per-chain seeds like engineFactory (sampling.h:19-42)
+struct Mt {
+    uint32_t mt[624];
+    int idx;
+    explicit Mt(uint32_t seed) {
+        mt[0] = seed;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int k = 0; k < 624; ++k) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+};
+
+// imd.ofg -> CSR (Gibbs.cpp:101-137); N1 = number of lines after the header
+void load_ofg(const std::string& path, int M, uint64_t& N0, std::vector<uint64_t>& row_ptr, std::vector<int32_t>& sid,
+              std::vector<double>& conprb) {
+    std::vector<char> buf = slurp(path, false);
+    if (buf.empty()) die("Cannot open " + path + "!");
+    buf.push_back('\n');
+    const char* p = buf.data();
+    const char* end = p + buf.size();
+    char* q = nullptr;
+    const long long m = strtoll(p, &q, 10);
+    p = q;
+    N0 = strtoull(p, &q, 10);
+    p = q;
+    if (m != M) die("M in " + path + " is not consistent with the reference!");
+    while (p < end && *p != '\n') ++p;
+    ++p;
+    row_ptr.assign(1, 0);
+    while (p < end) {
+        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+        if (!eol) break;
+        if (eol == p && eol + 1 >= end) break;  // the terminator we appended
+        while (p < eol) {
+            while (p < eol && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+            if (p >= eol) break;
+            const long s = strtol(p, &q, 10);
+            if (q == p) break;
+            p = q;
+            const double c = strtod(p, &q);
+            if (q == p) break;
+            p = q;
+            sid.push_back((int32_t)s);
+            conprb.push_back(c);
+        }
+        row_ptr.push_back(sid.size());
+        p = eol + 1;
+    }
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+    if (argc < 7) {
+        printf("Usage: rsem-run-gibbs reference_name imdName statName BURNIN NSAMPLES GAP [-p #Threads] [--seed seed] [--pseudo-count pseudo_count] [--prior file] [-q]\n");
+        printf("\n");
+        printf("Format of the prior file:\n");
+        printf("- One isoform's prior per line\n");
+        printf("- Priors must be in the same order as in the .ti file\n");
+        printf("- Priors for those to-be-omitted isoforms must be included as well\n");
+        printf("- Comments can be added after prior separated by space(s)\n");
+        exit(-1);
+    }
+    const std::string refName = argv[1], imdName = argv[2], statName = argv[3];
+    const int BURNIN = atoi(argv[4]), NSAMPLES = atoi(argv[5]), GAP = atoi(argv[6]);
+    int nThreads = 1;
+    bool hasSeed = false, quiet = false, has_prior = false;
+    uint32_t seed = 0;
+    double pseudoC = 1.0;
+    std::string fprior;
+    for (int i = 7; i < argc; ++i) {
+        if (!strcmp(argv[i], "-p") && i + 1 < argc) nThreads = atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "--seed") && i + 1 < argc) { hasSeed = true; seed = parse_seed(argv[i + 1]); }
+        if (!strcmp(argv[i], "--pseudo-count") && i + 1 < argc) pseudoC = atof(argv[i + 1]);
+        if (!strcmp(argv[i], "-q")) quiet = true;
+        if (!strcmp(argv[i], "--prior") && i + 1 < argc) { has_prior = true; fprior = argv[i + 1]; }
+    }
+    g_verbose = !quiet;
+    if (!(NSAMPLES > 1)) die("NSAMPLES must be larger than 1, otherwise the posterior variance cannot be calculated!");
+    if (GAP < 1) die("GAP must be at least 1!");
+    if (nThreads > NSAMPLES) {
+        nThreads = NSAMPLES;
+        fprintf(stderr, "Warning: Number of samples is less than number of threads! Change the number of threads to %d!\n", nThreads);
+    }
+    if (nThreads < 1) nThreads = 1;
+
+    // load_data
+    RefData refs;
+    load_refs(refName + ".seq", false, refs);
+    const int M = refs.M;
+    uint64_t N0 = 0;
+    std::vector<uint64_t> row_ptr;
+    std::vector<int32_t> sid;
+    std::vector<double> conprb;
+    load_ofg(imdName + ".ofg", M, N0, row_ptr, sid, conprb);
+    const uint64_t N1 = row_ptr.size() - 1;
+    if (g_verbose) printf("Loading data is finished!\n");
+
+    std::vector<int> gi, gt, ta;
+    load_groups(refName + ".grp", gi);
+    const int m = (int)gi.size() - 1;
+    const bool alleleS = load_allele_groups(refName, gt, ta);
+    if (g_verbose) printf("Loading group information is finished!\n");
+
+    // load_omit_info (Gibbs.cpp:152-167)
+    std::vector<int32_t> init_counts(M + 1, 0);
+    double totc = M + 1;
+    {
+        FILE* fi = fopen((imdName + ".omit").c_str(), "r");
+        if (!fi) die("Cannot open " + imdName + ".omit!");
+        int tid;
+        while (fscanf(fi, "%d", &tid) == 1) {
+            if (tid < 0 || tid > M) die("Invalid transcript id in " + imdName + ".omit!");
+            init_counts[tid] = -1;
+            --totc;
+        }
+        fclose(fi);
+    }
+    totc = totc * pseudoC + N0 + N1;
+    std::vector<double> alpha(M + 1, pseudoC);
+    if (has_prior) {  // load_prior_info (Gibbs.cpp:171-194)
+        alpha.assign(M + 1, 0.0);
+        FILE* fi = fopen(fprior.c_str(), "r");
+        if (!fi) die("Cannot open " + fprior + "!");
+        char line[4096];
+        for (int i = 1; i <= M; ++i) {
+            double prior = 0.0;
+            if (fgets(line, sizeof line, fi)) sscanf(line, "%lf", &prior);
+            if (init_counts[i] == 0) alpha[i] = prior;
+        }
+        fclose(fi);
+        totc = 1;
+        for (int i = 1; i <= M; ++i)
+            if (init_counts[i] == 0) totc += alpha[i];
+        totc += N0 + N1;
+    }
+
+    // init_model_related: eel from the .model's gld, mw copy
+    int model_type = 0;
+    LenDistH gld;
+    std::vector<double> mw, eel;
+    HostModel::read_for_gibbs(statName + ".model", M, model_type, gld, mw);
+    calc_eel(refs, gld, eel);
+
+    if (g_verbose) printf("Gibbs started!\n");
+
+    // init(): samples per chain and per-chain engines (Gibbs.cpp:207-254)
+    std::vector<int32_t> chain_samples(nThreads);
+    std::vector<uint32_t> chain_seeds(nThreads);
+    {
+        const int quotient = NSAMPLES / nThreads, left = NSAMPLES % nThreads;
+        Mt seedEngine(hasSeed ? seed : (uint32_t)time(NULL));
+        std::set<uint32_t> used;
+        for (int i = 0; i < nThreads; ++i) {
+            chain_samples[i] = quotient + (i < left ? 1 : 0);
+            uint32_t s;
+            do { s = seedEngine.next(); } while (used.count(s));
+            used.insert(s);
+            chain_seeds[i] = s;
+        }
+    }
+    if (g_verbose) printf("Initialization finished!\n");
+
+    rsem_b200_ctx* ctx = nullptr;
+    const char* dev = getenv("RSEM_B200_DEVICE");
+    check_rc(rsem_b200_ctx_create(dev ? atoi(dev) : 0, &ctx), "ctx_create");
+    check_rc(rsem_b200_gibbs_upload(ctx, N1, sid.size(), M, row_ptr.data(), sid.data(), conprb.data()), "gibbs_upload");
+
+    rsem_b200_gibbs_params gp;
+    memset(&gp, 0, sizeof gp);
+    gp.M = M; gp.burnin = BURNIN; gp.gap = GAP; gp.n_chains = nThreads;
+    gp.chain_samples = chain_samples.data();
+    gp.chain_seeds = chain_seeds.data();
+    gp.n0 = (double)N0;
+    gp.init_counts = init_counts.data();
+    gp.pseudo_counts = alpha.data();
+    gp.totc = totc;
+    gp.eel = eel.data();
+    gp.mw = mw.data();
+    gp.n_genes = m;
+    gp.gene_start = gi.data();
+    std::vector<int32_t> cvs((size_t)NSAMPLES * (M + 1));
+    std::vector<double> sum_c(M + 1), sum_c2(M + 1), sum_tpm(M + 1), sum_fpkm(M + 1), sum_g2(m);
+    rsem_b200_gibbs_out go;
+    go.count_vectors = cvs.data();
+    go.sum_c = sum_c.data(); go.sum_c2 = sum_c2.data(); go.sum_tpm = sum_tpm.data(); go.sum_fpkm = sum_fpkm.data();
+    go.sum_gene_c2 = sum_g2.data();
+    check_rc(rsem_b200_gibbs_run(ctx, &gp, &go), "gibbs_run");
+    rsem_b200_ctx_destroy(ctx);
+
+    // imd.countvectors<t> (Gibbs.cpp:257-262)
+    {
+        size_t at = 0;
+        static char buf[1 << 20];
+        for (int t = 0; t < nThreads; ++t) {
+            FILE* fo = fopen((imdName + ".countvectors" + std::to_string(t)).c_str(), "w");
+            if (!fo) die("Cannot open " + imdName + ".countvectors" + std::to_string(t) + " for writing!");
+            setvbuf(fo, buf, _IOFBF, sizeof buf);
+            for (int s = 0; s < chain_samples[t]; ++s, ++at) {
+                const int32_t* c = &cvs[at * (M + 1)];
+                for (int i = 0; i < M; ++i) fprintf(fo, "%d ", c[i]);
+                fprintf(fo, "%d\n", c[M]);
+            }
+            fclose(fo);
+        }
+    }
+
+    // release(): means and unbiased variances (Gibbs.cpp:399-422)
+    std::vector<double> pme_c(M + 1), pve_c(M + 1), pme_tpm(M + 1), pme_fpkm(M + 1), pve_g(m), pve_t;
+    for (int i = 0; i <= M; ++i) {
+        pme_c[i] = sum_c[i] / NSAMPLES;
+        pve_c[i] = (sum_c2[i] - double(NSAMPLES) * pme_c[i] * pme_c[i]) / double(NSAMPLES - 1);
+        if (pve_c[i] < 0.0) pve_c[i] = 0.0;
+        pme_tpm[i] = sum_tpm[i] / NSAMPLES;
+        pme_fpkm[i] = sum_fpkm[i] / NSAMPLES;
+    }
+    for (int i = 0; i < m; ++i) {
+        double g = 0.0;
+        for (int j = gi[i]; j < gi[i + 1]; ++j) g += pme_c[j];
+        pve_g[i] = (sum_g2[i] - double(NSAMPLES) * g * g) / double(NSAMPLES - 1);
+        if (pve_g[i] < 0.0) pve_g[i] = 0.0;
+    }
+    if (alleleS) {  // allele-level variances from the kept count vectors (Gibbs.cpp:338-345, 414-421)
+        const int m_trans = (int)ta.size() - 1;
+        pve_t.assign(m_trans, 0.0);
+        for (int s = 0; s < NSAMPLES; ++s) {
+            const int32_t* c = &cvs[(size_t)s * (M + 1)];
+            for (int i = 0; i < m_trans; ++i) {
+                double x = 0.0;
+                for (int j = ta[i]; j < ta[i + 1]; ++j) x += c[j];
+                pve_t[i] += x * x;
+            }
+        }
+        for (int i = 0; i < m_trans; ++i) {
+            double x = 0.0;
+            for (int j = ta[i]; j < ta[i + 1]; ++j) x += pme_c[j];
+            pve_t[i] = (pve_t[i] - double(NSAMPLES) * x * x) / double(NSAMPLES - 1);
+            if (pve_t[i] < 0.0) pve_t[i] = 0.0;
+        }
+    }
+    if (g_verbose) printf("Gibbs finished!\n");
+    write_results_gibbs(refName, imdName, M, pme_c, pme_fpkm, pme_tpm, pve_c, pve_g, pve_t);
+    return 0;
+}
