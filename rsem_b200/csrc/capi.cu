@@ -31,6 +31,7 @@ int upload(rsem_b200_ctx* ctx, T** dst, const T* src, size_t n) {
 void free_hits(rsem_b200_ctx* c) {
     dev_free(c, &c->row_ptr, c->N + 1);
     dev_free(c, &c->sid, c->H);
+    if (c->sid_abs) dev_free(c, &c->sid_abs, c->H);
     if (c->pos) dev_free(c, &c->pos, c->H);
     if (c->insertL) dev_free(c, &c->insertL, c->H);
     dev_free(c, &c->conprb, c->H);
@@ -90,6 +91,8 @@ int ensure_stats(rsem_b200_ctx* c, int n) {
 }
 
 int finish_matrix_setup(rsem_b200_ctx* ctx) {
+    if (int rc = dev_alloc(ctx, &ctx->sid_abs, (size_t)ctx->H)) return rc;
+    if (int rc = em_make_abs_sid(ctx)) return rc;
     if (int rc = dev_alloc(ctx, &ctx->theta, (size_t)ctx->M + 1)) return rc;
     if (int rc = dev_alloc(ctx, &ctx->count, (size_t)ctx->M + 1)) return rc;
     RB_CUDA(cudaMemsetAsync(ctx->theta, 0, ((size_t)ctx->M + 1) * sizeof(double), ctx->stream));

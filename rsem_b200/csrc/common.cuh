@@ -111,7 +111,8 @@ struct rsem_b200_ctx {
     int M = 0;
     uint32_t max_deg = 0;
     uint64_t* row_ptr = nullptr;
-    int32_t* sid = nullptr;
+    int32_t* sid = nullptr;      // signed: sign = strand (K1 / K3)
+    int32_t* sid_abs = nullptr;  // |sid|: the stream K2 reads
     int32_t* pos = nullptr;
     int32_t* insertL = nullptr;
     double* conprb = nullptr;
@@ -124,7 +125,8 @@ struct rsem_b200_ctx {
     uint64_t* tile_row = nullptr;
     uint64_t* tile_hit = nullptr;
     uint32_t n_tiles = 0;
-    int group = 16;       // lanes cooperating on one row
+    int group = 16;       // lanes cooperating on one row (K1 / K3 / direct K2)
+    int tma_group = 4;    // lanes per row in phase B of the staged K2
     int variant = 0;      // 0 auto, 1 TMA-staged, 2 direct
 
     // EM state
@@ -188,6 +190,7 @@ int em_build_tiles(rsem_b200_ctx* ctx);
 int em_launch_estep(rsem_b200_ctx* ctx, bool write_post);
 int em_launch_theta_update(rsem_b200_ctx* ctx, double n0, int round, int min_round, int max_round, int stats_slot);
 int em_max_degree(rsem_b200_ctx* ctx, uint32_t* max_deg);
+int em_make_abs_sid(rsem_b200_ctx* ctx);
 
 // model_kernels.cu
 int model_launch_conprb(rsem_b200_ctx* ctx);

@@ -8,13 +8,13 @@
 //   * the hit matrix is SoA CSR in HBM (row_ptr u64, sid i32, conprb f64, ncpv f64); one pass
 //     streams 12 B per hit + 16 B per read, nothing else comes from HBM (theta / count live in L2);
 //   * rows are cut into byte-balanced tiles once per upload; a persistent CTA per SM walks its
-//     tiles through a 4-stage shared-memory ring filled by 1-D bulk-async copies (TMA,
+//     tiles through a 3-stage shared-memory ring filled by 1-D bulk-async copies (TMA,
 //     cp.async.bulk + mbarrier complete_tx), so the bytes in flight per SM are set by the ring
 //     depth, not by occupancy or by the dependent row_ptr -> hits -> theta load chain;
-//   * a row is reduced by a group of G lanes (G = 4..32, chosen from the mean degree) with
-//     xor-shuffles; normalised weights go to the count vector with red.global.add.f64
-//     (L2-resident), the noise entry count[0] - which every row touches - is privatised in a
-//     register and flushed once per CTA.
+//   * products theta * conprb and the count updates are computed flat over hits (thread = hit), row
+//     sums by small lane groups (G ~ degree / 5) with xor-shuffles; normalised weights go to the
+//     count vector with red.global.add.f64 (L2-resident), the noise entry count[0] - which every row
+//     touches - is privatised in a register and flushed once per CTA.
 //
 // Clamp semantics are the reference's: a term < 1e-300 is 0, a row whose sum < 1e-300
 // contributes nothing (EM.cpp:212,219,223).
@@ -35,9 +35,9 @@ namespace {
 // tile geometry of the TMA-staged kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kThreads = 512;
-constexpr int kStages = 4;
-constexpr int kTileHitCap = 3072;  // max hits a stage can hold
-constexpr int kTileRowCap = 384;   // max rows a stage can hold
+constexpr int kStages = 3;
+constexpr int kTileHitCap = 2304;  // max hits a stage can hold
+constexpr int kTileRowCap = 512;   // max rows a stage can hold (kThreads / G for the actual G)
 constexpr int kSidElems = kTileHitCap + 8;
 constexpr int kConElems = kTileHitCap + 4;
 constexpr int kRowElems = kTileRowCap + 4;
@@ -114,6 +114,8 @@ __device__ __forceinline__ double group_sum(double v) {
     for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+template <>
+__device__ __forceinline__ double group_sum<1>(double v) { return v; }
 
 __device__ __forceinline__ unsigned round16(unsigned bytes) { return (bytes + 15u) & ~15u; }
 
@@ -216,57 +218,22 @@ __device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage
     bulk_load(st.ncp, a.ncpv + rs2, b_nc, bar);
 }
 
-// Phase B of the staged kernel: one row, reduced by the G lanes of a group, reading the products
-// f = theta[sid] * conprb that phase A left in shared memory (already clamped).
+// ------------------------------------------------------------------------------------------------
+// K2, TMA-staged.  Persistent CTAs, two per SM (so one CTA's barrier bubbles are filled by the
+// other), kThreads threads each.  A tile (<= kTileHitCap hits, <= kThreads / G rows) goes through
+// three CTA-wide phases:
+//   A  flat over hits (thread = hit, stride kThreads):  f = theta[|sid|] * conprb, clamped, written
+//      over the conprb slot.  All loads are independent (4 gathers in flight per thread) and
+//      consecutive threads touch consecutive transcript ids (isoforms of a gene are adjacent), so a
+//      warp-wide gather needs only a few L2 sectors.
+//   B  one row per group of G lanes (G ~ degree / 5, so every row of the tile is handled in ONE
+//      pass with all lanes busy):  row sum incl. the noise term, reciprocal, f <- f / sum in place.
+//   C  flat over hits again:  red.global.add.f64 of the normalised weight on the count vector -
+//      consecutive threads -> consecutive addresses -> few sectors per request - and, for the
+//      posterior variant, a coalesced store.
+// ------------------------------------------------------------------------------------------------
 template <int G, bool WRITE_POST>
-__device__ __forceinline__ double reduce_row(bool valid, int g, unsigned d, const int* sp, const double* fp, double nc,
-                                             double theta0, double* count, double* post_row, double* post0_row) {
-    double fa = 0.0, fb = 0.0, part = 0.0, f0 = 0.0;
-    if (valid) {
-        if (g < d) fa = fp[g];
-        if (g + G < d) fb = fp[g + G];
-        part = fa + fb;
-        for (unsigned j = g + 2 * G; j < d; j += G) part += fp[j];
-        if (g == 0) {
-            f0 = theta0 * nc;
-            if (f0 < kEpsilon) f0 = 0.0;
-            part += f0;
-        }
-    }
-    const double sum = group_sum<G>(part);
-    if (!valid) return 0.0;
-    double acc0 = 0.0;
-    if (sum >= kEpsilon) {
-        const double inv = 1.0 / sum;
-        if (g == 0) {
-            acc0 = f0 * inv;
-            if (WRITE_POST) *post0_row = acc0;
-        }
-        if (g < d) {
-            const double w = fa * inv;
-            if (fa != 0.0) red_add_f64(count + abs(sp[g]), w);
-            if (WRITE_POST) post_row[g] = w;
-        }
-        if (g + G < d) {
-            const double w = fb * inv;
-            if (fb != 0.0) red_add_f64(count + abs(sp[g + G]), w);
-            if (WRITE_POST) post_row[g + G] = w;
-        }
-        for (unsigned j = g + 2 * G; j < d; j += G) {
-            const double f = fp[j];
-            const double w = f * inv;
-            if (f != 0.0) red_add_f64(count + abs(sp[j]), w);
-            if (WRITE_POST) post_row[j] = w;
-        }
-    } else if (WRITE_POST) {
-        if (g == 0) *post0_row = 0.0;
-        for (unsigned j = g; j < d; j += G) post_row[j] = 0.0;
-    }
-    return acc0;
-}
-
-template <int G, bool WRITE_POST>
-__global__ void __launch_bounds__(kThreads, 1) estep_tma_kernel(const EstepArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
     if (*a.done_flag) return;
@@ -284,12 +251,9 @@ __global__ void __launch_bounds__(kThreads, 1) estep_tma_kernel(const EstepArgs 
         }
     }
 
-    constexpr int kGroupsPerWarp = 32 / G;
-    constexpr int kWarps = kThreads / 32;
     constexpr int kUnroll = 4;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int g = lane % G;
-    const int group_in_warp = lane / G;
+    const int g = tid % G;
+    const unsigned row_in_tile = tid / G;
     const double theta0 = __ldg(a.theta);
     double acc0 = 0.0;
 
@@ -303,55 +267,71 @@ __global__ void __launch_bounds__(kThreads, 1) estep_tma_kernel(const EstepArgs 
         const unsigned long long rs = a.tile_row[k], re = a.tile_row[k + 1];
         const unsigned long long hs = a.tile_hit[k];
         const unsigned nr = (unsigned)(re - rs);
+        const unsigned nh = (unsigned)(a.tile_hit[k + 1] - hs);
         const unsigned roff = (unsigned)(rs & 1ull);
-        int* s_sid = st.sid + (unsigned)(hs & 3ull);      // element 0 = first hit of the tile
+        const int* s_sid = st.sid + (unsigned)(hs & 3ull);  // element 0 = first hit of the tile
         double* s_con = st.con + (unsigned)(hs & 1ull);
-        // this warp's contiguous share of the tile's rows (and therefore of its hits)
-        const unsigned r0 = (nr * (unsigned)warp) / kWarps, r1 = (nr * (unsigned)(warp + 1)) / kWarps;
-        if (r1 > r0) {
-            const unsigned h0 = (unsigned)(st.rp[roff + r0] - hs), h1 = (unsigned)(st.rp[roff + r1] - hs);
-            // phase A: f = theta[|sid|] * conprb for every hit, flat over the hit range (all loads
-            // independent, kUnroll gathers in flight per lane), written over the conprb slot
-            for (unsigned h = h0 + lane; h < h1; h += 32 * kUnroll) {
-                int t[kUnroll];
-                double c[kUnroll], th[kUnroll];
+
+        // ---- phase A
+        for (unsigned h = tid; h < nh; h += kThreads * kUnroll) {
+            int t[kUnroll];
+            double c[kUnroll], th[kUnroll];
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const unsigned j = h + 32 * u;
-                    t[u] = j < h1 ? abs(s_sid[j]) : 0;
-                }
+            for (int u = 0; u < kUnroll; ++u) {
+                const unsigned j = h + kThreads * u;
+                t[u] = j < nh ? s_sid[j] : 0;
+            }
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) th[u] = __ldg(a.theta + t[u]);
+            for (int u = 0; u < kUnroll; ++u) th[u] = __ldg(a.theta + t[u]);
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const unsigned j = h + 32 * u;
-                    c[u] = j < h1 ? s_con[j] : 0.0;
-                }
+            for (int u = 0; u < kUnroll; ++u) {
+                const unsigned j = h + kThreads * u;
+                c[u] = j < nh ? s_con[j] : 0.0;
+            }
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const unsigned j = h + 32 * u;
-                    double f = th[u] * c[u];
-                    if (f < kEpsilon) f = 0.0;
-                    if (j < h1) s_con[j] = f;
+            for (int u = 0; u < kUnroll; ++u) {
+                const unsigned j = h + kThreads * u;
+                double f = th[u] * c[u];
+                if (f < kEpsilon) f = 0.0;
+                if (j < nh) s_con[j] = f;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase B (one pass when the tile has <= kThreads / G rows, which the tile builder aims for)
+        for (unsigned rbase = 0; rbase < nr; rbase += kThreads / G) {
+            const unsigned row = rbase + row_in_tile;
+            const bool valid = row < nr;
+            unsigned b = 0, e = 0;
+            double part = 0.0, f0 = 0.0;
+            if (valid) {
+                b = (unsigned)(st.rp[roff + row] - hs);
+                e = (unsigned)(st.rp[roff + row + 1] - hs);
+                for (unsigned j = b + g; j < e; j += G) part += s_con[j];
+                if (g == 0) {
+                    f0 = theta0 * st.ncp[roff + row];
+                    if (f0 < kEpsilon) f0 = 0.0;
+                    part += f0;
                 }
             }
-            __syncwarp();
-            // phase B: row sums by lane groups, normalised weights to the count vector
-            for (unsigned base = r0; base < r1; base += kGroupsPerWarp) {
-                const unsigned i = base + group_in_warp;
-                const bool valid = i < r1;
-                unsigned long long rp0 = hs, rp1 = hs;
-                double nc = 0.0;
-                if (valid) {
-                    rp0 = st.rp[roff + i];
-                    rp1 = st.rp[roff + i + 1];
-                    nc = st.ncp[roff + i];
+            const double sum = group_sum<G>(part);
+            if (valid) {
+                const double inv = sum >= kEpsilon ? 1.0 / sum : 0.0;
+                for (unsigned j = b + g; j < e; j += G) s_con[j] *= inv;
+                if (g == 0) {
+                    const double p0 = f0 * inv;
+                    acc0 += p0;
+                    if (WRITE_POST) a.post0[rs + row] = p0;
                 }
-                const unsigned d = (unsigned)(rp1 - rp0), off = (unsigned)(rp0 - hs);
-                acc0 += reduce_row<G, WRITE_POST>(valid, g, d, s_sid + off, s_con + off, nc, theta0, a.count,
-                                                  WRITE_POST ? a.post + rp0 : nullptr,
-                                                  WRITE_POST ? a.post0 + rs + i : nullptr);
             }
+        }
+        __syncthreads();
+
+        // ---- phase C
+        for (unsigned j = tid; j < nh; j += kThreads) {
+            const double w = s_con[j];
+            if (w != 0.0) red_add_f64(a.count + s_sid[j], w);
+            if (WRITE_POST) a.post[hs + j] = w;
         }
         fence_proxy_async();  // generic-proxy writes to the stage precede its next bulk-async fill
         __syncthreads();      // every thread is done with stage s
@@ -418,6 +398,15 @@ __global__ void tile_bounds_kernel(const unsigned long long* row_ptr, unsigned l
     tile_row[k] = lo;
 }
 
+__global__ void max_diff_kernel(const unsigned long long* v, unsigned long long n, unsigned int* out) {
+    unsigned int m = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        m = max(m, (unsigned)(v[i + 1] - v[i]));
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 __global__ void gather_u64_kernel(const unsigned long long* src, const unsigned long long* idx, unsigned long long n,
                                   unsigned long long* out) {
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -425,12 +414,14 @@ __global__ void gather_u64_kernel(const unsigned long long* src, const unsigned 
 }
 
 __global__ void max_degree_kernel(const unsigned long long* row_ptr, unsigned long long N, unsigned int* out) {
-    unsigned int m = 0;
+    unsigned int m = 0, has_empty = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < N;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long d = row_ptr[i + 1] - row_ptr[i];
         m = max(m, d > 0xffffffffull ? 0xffffffffu : (unsigned)d);
+        if (d == 0) has_empty = 1;
     }
+    if (has_empty) out[1] = 1;
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
@@ -513,7 +504,7 @@ int launch_variant(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
         const size_t smem = sizeof(SmemLayout);
         RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         (void)attr_set;
-        unsigned grid = ctx->sm_count;
+        unsigned grid = ctx->sm_count * 2;
         if (grid > a.n_tiles) grid = a.n_tiles ? a.n_tiles : 1;
         kern<<<grid, kThreads, smem, ctx->stream>>>(a);
     } else {
@@ -530,6 +521,16 @@ int launch_variant(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
 
 template <bool WP>
 int launch_group(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
+    if (tma) {
+        switch (ctx->tma_group) {
+            case 1: return launch_variant<1, WP>(ctx, a, true);
+            case 2: return launch_variant<2, WP>(ctx, a, true);
+            case 4: return launch_variant<4, WP>(ctx, a, true);
+            case 8: return launch_variant<8, WP>(ctx, a, true);
+            case 16: return launch_variant<16, WP>(ctx, a, true);
+            default: return launch_variant<32, WP>(ctx, a, true);
+        }
+    }
     switch (ctx->group) {
         case 4: return launch_variant<4, WP>(ctx, a, tma);
         case 8: return launch_variant<8, WP>(ctx, a, tma);
@@ -540,16 +541,30 @@ int launch_group(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
 
 }  // namespace
 
-int em_max_degree(rsem_b200_ctx* ctx, uint32_t* max_deg) {
+__global__ void abs_kernel(const int* in, int* out, unsigned long long n) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        out[i] = abs(in[i]);
+}
+
+int em_make_abs_sid(rsem_b200_ctx* ctx) {
+    if (ctx->H == 0) return 0;
+    abs_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->sid, ctx->sid_abs, ctx->H);
+    RB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+int em_max_degree(rsem_b200_ctx* ctx, uint32_t* max_deg) {  // max_deg[0] = longest row, max_deg[1] = 1 if some row is empty
     unsigned int* d = nullptr;
-    RB_CUDA(cudaMalloc(&d, sizeof(unsigned int)));
-    RB_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned int), ctx->stream));
+    RB_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned int)));
+    RB_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned int), ctx->stream));
     if (ctx->N > 0) {
         max_degree_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(
             reinterpret_cast<const unsigned long long*>(ctx->row_ptr), ctx->N, d);
         ctx->launches++;
     }
-    RB_CUDA(cudaMemcpyAsync(max_deg, d, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaMemcpyAsync(max_deg, d, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(d);
     return 0;
@@ -561,27 +576,52 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
     ctx->n_tiles = 0;
     if (ctx->N == 0) return 0;
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (int rc = em_max_degree(ctx, &ctx->max_deg)) return rc;
+    uint32_t deg_info[2] = {0, 0};
+    if (int rc = em_max_degree(ctx, deg_info)) return rc;
+    ctx->max_deg = deg_info[0];
 
     // lanes per row from the mean degree (+1 for the noise entry)
     const double mean_deg = (double)ctx->H / (double)ctx->N + 1.0;
     ctx->group = mean_deg <= 5.0 ? 4 : mean_deg <= 11.0 ? 8 : mean_deg <= 26.0 ? 16 : 32;
+    // lanes per row in phase B of the staged kernel: about one lane per 5 hits
+    ctx->tma_group = mean_deg <= 7.0 ? 1 : mean_deg <= 14.0 ? 2 : mean_deg <= 28.0 ? 4 : mean_deg <= 56.0 ? 8 : mean_deg <= 112.0 ? 16 : 32;
     if (const char* e = getenv("RSEM_B200_GROUP")) {  // tuning knob (profiling only)
         const int v = atoi(e);
-        if (v == 4 || v == 8 || v == 16 || v == 32) ctx->group = v;
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ctx->tma_group = v;
     }
 
-    if (ctx->max_deg > (uint32_t)kTileHitCap / 2) return 0;  // rows too long for a stage: direct kernel only
-    const unsigned long long W = kTileHitCap - ctx->max_deg;
-    const unsigned long long C = (W + kTileRowCap - 2) / (kTileRowCap - 1);
-    const unsigned long long total = ctx->H + C * ctx->N;
-    const unsigned long long n_raw = total / W + 1;
+    // rows too long for a stage, or rows without hits (never produced by rsem-parse-alignments,
+    // HitContainer.h:67 asserts tot > 0): direct kernel only
+    if (ctx->max_deg > (uint32_t)kTileHitCap / 3 || deg_info[1]) return 0;
+    // hits per tile <= W + max_deg: keep that within one fully unrolled phase-A pass (4 hits per thread)
+    // when rows are short enough, otherwise within the stage capacity
+    unsigned long long W = ctx->max_deg <= 256 ? 4ull * kThreads - ctx->max_deg : (unsigned long long)kTileHitCap - ctx->max_deg;
+    // rows per tile <= W / C + 1 must fit the stage's row arrays; start from the byte-balanced weight
+    // (a row costs about as much traffic as a hit) and grow C only for matrices with very short rows
+    unsigned long long C = 1, n_raw = 0;
     unsigned long long* raw = nullptr;
-    RB_CUDA(cudaMalloc(&raw, (n_raw + 1) * sizeof(unsigned long long)));
-    tile_bounds_kernel<<<(unsigned)((n_raw + 1 + 255) / 256), 256, 0, ctx->stream>>>(
-        reinterpret_cast<const unsigned long long*>(ctx->row_ptr), ctx->N, W, C, n_raw, raw);
-    RB_CUDA(cudaGetLastError());
-    ctx->launches++;
+    for (;;) {
+        const unsigned long long total = ctx->H + C * ctx->N;
+        n_raw = total / W + 1;
+        RB_CUDA(cudaMalloc(&raw, (n_raw + 1) * sizeof(unsigned long long)));
+        tile_bounds_kernel<<<(unsigned)((n_raw + 1 + 255) / 256), 256, 0, ctx->stream>>>(
+            reinterpret_cast<const unsigned long long*>(ctx->row_ptr), ctx->N, W, C, n_raw, raw);
+        RB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        unsigned int* d_max = nullptr;
+        unsigned int h_max = 0;
+        RB_CUDA(cudaMalloc(&d_max, sizeof(unsigned int)));
+        RB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned int), ctx->stream));
+        max_diff_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(raw, n_raw, d_max);
+        ctx->launches++;
+        RB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        RB_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_max);
+        if (h_max <= (unsigned)kTileRowCap) break;
+        cudaFree(raw);
+        raw = nullptr;
+        C *= 2;
+    }
     // drop empty tiles: consecutive equal boundaries
     thrust::device_ptr<unsigned long long> p(raw);
     auto end = thrust::unique(thrust::cuda::par.on(ctx->stream), p, p + n_raw + 1);
@@ -606,7 +646,7 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
 int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
     EstepArgs a;
     a.row_ptr = reinterpret_cast<const unsigned long long*>(ctx->row_ptr);
-    a.sid = ctx->sid;
+    a.sid = ctx->sid_abs;
     a.conprb = ctx->conprb;
     a.ncpv = ctx->ncpv;
     a.theta = ctx->theta;
