@@ -172,6 +172,8 @@ int dev_alloc(rsem_b200_ctx* ctx, T** p, size_t n) {
     void* q = nullptr;
     cudaError_t e = cudaMalloc(&q, bytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    // the padding is read (never used) by the pair-wise phases of the staged E-step: keep it defined
+    cudaMemset(static_cast<char*>(q) + n * sizeof(T), 0, 256);
     ctx->dev_bytes += bytes;
     *p = static_cast<T*>(q);
     return 0;

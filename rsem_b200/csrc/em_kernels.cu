@@ -50,9 +50,15 @@ struct __align__(16) Stage {
 };
 static_assert(sizeof(Stage) % 16 == 0, "stage must keep 16 B alignment");
 
+struct TileDesc {  // written by the producer thread when it issues the tile, read by everyone after the wait
+    unsigned long long rs, hs;
+    unsigned nr, nh;
+};
+
 struct SmemLayout {
     Stage stage[kStages];
     unsigned long long full_bar[kStages];
+    TileDesc desc[kStages];
     double red[kThreads / 32];
 };
 
@@ -203,9 +209,14 @@ __device__ __forceinline__ void flush_count0(double acc0, double* red_smem, doub
 // ------------------------------------------------------------------------------------------------
 // K2, TMA-staged.  grid = #SMs (persistent), block = kThreads.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage& st, unsigned long long* bar) {
+__device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage& st, unsigned long long* bar,
+                                           TileDesc& desc) {
     const unsigned long long rs = a.tile_row[k], re = a.tile_row[k + 1];
     const unsigned long long hs = a.tile_hit[k], he = a.tile_hit[k + 1];
+    desc.rs = rs;
+    desc.hs = hs;
+    desc.nr = (unsigned)(re - rs);
+    desc.nh = (unsigned)(he - hs);
     const unsigned long long hs4 = hs & ~3ull, hs2 = hs & ~1ull, rs2 = rs & ~1ull;
     const unsigned b_sid = round16((unsigned)(he - hs4) * 4u);
     const unsigned b_con = round16((unsigned)(he - hs2) * 8u);
@@ -247,11 +258,12 @@ __global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             const unsigned k = blockIdx.x + s * gridDim.x;
-            if (k < a.n_tiles) issue_tile(a, k, sm.stage[s], &sm.full_bar[s]);
+            if (k < a.n_tiles) issue_tile(a, k, sm.stage[s], &sm.full_bar[s], sm.desc[s]);
         }
     }
 
-    constexpr int kUnroll = 4;
+    constexpr int kPairs = 2;  // pairs of hits per thread and phase-A pass (4 gathers in flight)
+    constexpr int kSlots = 8;  // hits a lane keeps in registers in phase B
     const int g = tid % G;
     const unsigned row_in_tile = tid / G;
     const double theta0 = __ldg(a.theta);
@@ -264,36 +276,50 @@ __global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs 
         Stage& st = sm.stage[s];
         mbar_wait(&sm.full_bar[s], parity);
 
-        const unsigned long long rs = a.tile_row[k], re = a.tile_row[k + 1];
-        const unsigned long long hs = a.tile_hit[k];
-        const unsigned nr = (unsigned)(re - rs);
-        const unsigned nh = (unsigned)(a.tile_hit[k + 1] - hs);
+        const unsigned long long rs = sm.desc[s].rs, hs = sm.desc[s].hs;
+        const unsigned nr = sm.desc[s].nr, nh = sm.desc[s].nh;
         const unsigned roff = (unsigned)(rs & 1ull);
-        const int* s_sid = st.sid + (unsigned)(hs & 3ull);  // element 0 = first hit of the tile
-        double* s_con = st.con + (unsigned)(hs & 1ull);
+        // Flat phases work on 16-byte aligned PAIRS of hits: pair p = elements 2p, 2p + 1 of the
+        // conprb stage array (which starts at the even hit index hs & ~1) and elements
+        // sid_shift + 2p, + 1 of the sid stage array (which starts at hs & ~3).  The first / last pair
+        // may contain one hit of the neighbouring tile: computing its product is harmless, counting it
+        // is not, so phase C masks by index.
+        const unsigned con_lead = (unsigned)(hs & 1ull);          // elements before the tile's first hit
+        const unsigned sid_shift = (unsigned)(hs & 2ull);         // (hs & ~1) - (hs & ~3)
+        const unsigned n_pairs = (con_lead + nh + 1) >> 1;
+        double2* con2 = reinterpret_cast<double2*>(st.con);
+        const uint2* sid2 = reinterpret_cast<const uint2*>(st.sid + sid_shift);
+        double* s_con = st.con + con_lead;  // element 0 = first hit of the tile (phase B)
 
         // ---- phase A
-        for (unsigned h = tid; h < nh; h += kThreads * kUnroll) {
-            int t[kUnroll];
-            double c[kUnroll], th[kUnroll];
+        for (unsigned p0 = tid; p0 < n_pairs; p0 += kThreads * kPairs) {
+            uint2 t[kPairs];
+            double2 c[kPairs];
+            double th[2 * kPairs];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const unsigned j = h + kThreads * u;
-                t[u] = j < nh ? s_sid[j] : 0;
+            for (int u = 0; u < kPairs; ++u) {
+                const unsigned p = p0 + kThreads * u;
+                t[u] = p < n_pairs ? sid2[p] : make_uint2(0u, 0u);
             }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) th[u] = __ldg(a.theta + t[u]);
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const unsigned j = h + kThreads * u;
-                c[u] = j < nh ? s_con[j] : 0.0;
+            for (int u = 0; u < kPairs; ++u) {
+                th[2 * u] = __ldg(a.theta + t[u].x);
+                th[2 * u + 1] = __ldg(a.theta + t[u].y);
             }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const unsigned j = h + kThreads * u;
-                double f = th[u] * c[u];
-                if (f < kEpsilon) f = 0.0;
-                if (j < nh) s_con[j] = f;
+            for (int u = 0; u < kPairs; ++u) {
+                const unsigned p = p0 + kThreads * u;
+                c[u] = p < n_pairs ? con2[p] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < kPairs; ++u) {
+                const unsigned p = p0 + kThreads * u;
+                double2 f;
+                f.x = th[2 * u] * c[u].x;
+                f.y = th[2 * u + 1] * c[u].y;
+                if (f.x < kEpsilon) f.x = 0.0;
+                if (f.y < kEpsilon) f.y = 0.0;
+                if (p < n_pairs) con2[p] = f;
             }
         }
         __syncthreads();
@@ -303,41 +329,60 @@ __global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs 
             const unsigned row = rbase + row_in_tile;
             const bool valid = row < nr;
             unsigned b = 0, e = 0;
+            double x[kSlots];
             double part = 0.0, f0 = 0.0;
             if (valid) {
                 b = (unsigned)(st.rp[roff + row] - hs);
                 e = (unsigned)(st.rp[roff + row + 1] - hs);
-                for (unsigned j = b + g; j < e; j += G) part += s_con[j];
-                if (g == 0) {
-                    f0 = theta0 * st.ncp[roff + row];
-                    if (f0 < kEpsilon) f0 = 0.0;
-                    part += f0;
-                }
+            }
+#pragma unroll
+            for (int q = 0; q < kSlots; ++q) {
+                const unsigned j = b + g + q * G;
+                x[q] = j < e ? s_con[j] : 0.0;
+            }
+            part = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+            for (unsigned j = b + g + kSlots * G; j < e; j += G) part += s_con[j];
+            if (valid && g == 0) {
+                f0 = theta0 * st.ncp[roff + row];
+                if (f0 < kEpsilon) f0 = 0.0;
+                part += f0;
             }
             const double sum = group_sum<G>(part);
-            if (valid) {
-                const double inv = sum >= kEpsilon ? 1.0 / sum : 0.0;
-                for (unsigned j = b + g; j < e; j += G) s_con[j] *= inv;
-                if (g == 0) {
-                    const double p0 = f0 * inv;
-                    acc0 += p0;
-                    if (WRITE_POST) a.post0[rs + row] = p0;
-                }
+            const double inv = sum >= kEpsilon ? 1.0 / sum : 0.0;
+#pragma unroll
+            for (int q = 0; q < kSlots; ++q) {
+                const unsigned j = b + g + q * G;
+                if (j < e) s_con[j] = x[q] * inv;
+            }
+            for (unsigned j = b + g + kSlots * G; j < e; j += G) s_con[j] *= inv;
+            if (valid && g == 0) {
+                const double p0 = f0 * inv;
+                acc0 += p0;
+                if (WRITE_POST) a.post0[rs + row] = p0;
             }
         }
         __syncthreads();
 
         // ---- phase C
-        for (unsigned j = tid; j < nh; j += kThreads) {
-            const double w = s_con[j];
-            if (w != 0.0) red_add_f64(a.count + s_sid[j], w);
-            if (WRITE_POST) a.post[hs + j] = w;
+        for (unsigned p = tid; p < n_pairs; p += kThreads) {
+            const double2 w = con2[p];
+            const uint2 t = sid2[p];
+            const unsigned j0 = 2 * p - con_lead;  // tile-local hit index of w.x (wraps for the lead-in element)
+            if (j0 < nh) {
+                if (w.x != 0.0) red_add_f64(a.count + t.x, w.x);
+                if (WRITE_POST) a.post[hs + j0] = w.x;
+            }
+            const unsigned j1 = j0 + 1;  // 0 for the lead-in pair
+            if (j1 < nh) {
+                if (w.y != 0.0) red_add_f64(a.count + t.y, w.y);
+                if (WRITE_POST) a.post[hs + j1] = w.y;
+            }
         }
         fence_proxy_async();  // generic-proxy writes to the stage precede its next bulk-async fill
         __syncthreads();      // every thread is done with stage s
         if (tid == 0) {
             const unsigned long long kn = (unsigned long long)k + (unsigned long long)kStages * gridDim.x;
-            if (kn < a.n_tiles) issue_tile(a, (unsigned)kn, st, &sm.full_bar[s]);
+            if (kn < a.n_tiles) issue_tile(a, (unsigned)kn, st, &sm.full_bar[s], sm.desc[s]);
         }
     }
     flush_count0(acc0, sm.red, a.count);
