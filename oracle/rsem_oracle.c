@@ -74,8 +74,14 @@ void ro_estep(uint64_t N, const uint64_t* row_ptr, const int32_t* sid, const dou
         }
         estep_range(lo, hi, row_ptr, sid, conprb, ncpv, theta, priv + (size_t)t * ((size_t)M + 1), post, post0);
     }
-    for (int t = 0; t < n_threads; ++t)
-        for (int32_t k = 0; k <= M; ++k) counts[k] += priv[(size_t)t * ((size_t)M + 1) + k];
+    /* the reference merges serially (EM.cpp:385-389); the port splits the merge over transcripts so that a
+     * bounded benchmark sample with many threads is not dominated by it */
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+    for (int32_t k = 0; k <= M; ++k) {
+        double acc = 0.0;
+        for (int t = 0; t < n_threads; ++t) acc += priv[(size_t)t * ((size_t)M + 1) + k];
+        counts[k] = acc;
+    }
     free(priv);
 #else
     estep_range(0, N, row_ptr, sid, conprb, ncpv, theta, counts, post, post0);
