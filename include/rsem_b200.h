@@ -219,7 +219,8 @@ int rsem_b200_launch_count(rsem_b200_ctx* ctx, uint64_t* launches);
 int rsem_b200_estep_timing(rsem_b200_ctx* ctx, double* total_ms, uint64_t* launches, int32_t reset);
 /* enable per-launch event timing of K2 (off by default: it adds two event records per round)    */
 int rsem_b200_set_profiling(rsem_b200_ctx* ctx, int32_t enabled);
-/* select the E/M kernel variant: 0 = auto, 1 = TMA-staged tiles, 2 = direct (no smem staging)  */
+/* select the E/M kernel variant: 0 = auto, 1 = CTA-staged tiles (TMA), 2 = direct (no smem staging),
+ * 3 = warp-pipelined tiles (TMA, no CTA barriers)                                                */
 int rsem_b200_set_estep_variant(rsem_b200_ctx* ctx, int32_t variant);
 
 #ifdef __cplusplus

@@ -58,11 +58,21 @@ void ro_estep(uint64_t N, const uint64_t* row_ptr, const int32_t* sid, const dou
 #ifdef _OPENMP
     /* contiguous read ranges with ~equal hit counts (EM.cpp:135-157), private count vectors,
      * serial merge (EM.cpp:385-389) */
-    double* priv = (double*)calloc((size_t)n_threads * ((size_t)M + 1), sizeof(double));
+    /* private count vectors are kept between calls (the reference allocates countvs[] once, EM.cpp:166-170) and
+     * zeroed by their owning thread (first touch places them on that thread's NUMA node) */
+    static double* priv = NULL;
+    static size_t priv_cap = 0;
+    const size_t need = (size_t)n_threads * ((size_t)M + 1);
+    if (priv_cap < need) {
+        free(priv);
+        priv = (double*)malloc(need * sizeof(double));
+        priv_cap = need;
+    }
     const uint64_t H = row_ptr[N];
 #pragma omp parallel num_threads(n_threads)
     {
         const int t = omp_get_thread_num(), T = omp_get_num_threads();
+        memset(priv + (size_t)t * ((size_t)M + 1), 0, sizeof(double) * ((size_t)M + 1));
         uint64_t lo, hi;
         { /* first row whose start >= t * H / T */
             uint64_t target = (uint64_t)((__uint128_t)H * t / T), a = 0, b = N;
@@ -82,7 +92,6 @@ void ro_estep(uint64_t N, const uint64_t* row_ptr, const int32_t* sid, const dou
         for (int t = 0; t < n_threads; ++t) acc += priv[(size_t)t * ((size_t)M + 1) + k];
         counts[k] = acc;
     }
-    free(priv);
 #else
     estep_range(0, N, row_ptr, sid, conprb, ncpv, theta, counts, post, post0);
 #endif

@@ -42,7 +42,9 @@ void free_hits(rsem_b200_ctx* c) {
     if (c->count) dev_free(c, &c->count, (size_t)c->M + 1);
     if (c->tile_row) { cudaFree(c->tile_row); c->tile_row = nullptr; }
     if (c->tile_hit) { cudaFree(c->tile_hit); c->tile_hit = nullptr; }
-    c->n_tiles = 0;
+    if (c->wtile_row) { cudaFree(c->wtile_row); c->wtile_row = nullptr; }
+    if (c->wtile_hit) { cudaFree(c->wtile_hit); c->wtile_hit = nullptr; }
+    c->n_tiles = c->n_wtiles = 0;
     c->N = c->H = 0;
     c->conprb_valid = false;
 }
@@ -579,7 +581,7 @@ int rsem_b200_set_profiling(rsem_b200_ctx* c, int32_t enabled) {
 }
 
 int rsem_b200_set_estep_variant(rsem_b200_ctx* c, int32_t v) {
-    RB_ARG(c && v >= 0 && v <= 2, "variant must be 0, 1 or 2");
+    RB_ARG(c && v >= 0 && v <= 3, "variant must be 0..3");
     c->variant = v;
     return 0;
 }

@@ -125,9 +125,12 @@ struct rsem_b200_ctx {
     uint64_t* tile_row = nullptr;
     uint64_t* tile_hit = nullptr;
     uint32_t n_tiles = 0;
+    uint64_t* wtile_row = nullptr;  // warp-pipelined kernel's own (smaller) tiles
+    uint64_t* wtile_hit = nullptr;
+    uint32_t n_wtiles = 0;
     int group = 16;       // lanes cooperating on one row (K1 / K3 / direct K2)
     int tma_group = 4;    // lanes per row in phase B of the staged K2
-    int variant = 0;      // 0 auto, 1 TMA-staged, 2 direct
+    int variant = 0;      // 0 auto, 1 CTA-staged, 2 direct, 3 warp-pipelined
 
     // EM state
     double* theta = nullptr;   // M + 1

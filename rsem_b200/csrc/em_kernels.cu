@@ -74,6 +74,9 @@ struct EstepArgs {
     const unsigned long long* tile_row;
     const unsigned long long* tile_hit;
     unsigned int n_tiles;
+    const unsigned long long* wtile_row;
+    const unsigned long long* wtile_hit;
+    unsigned int n_wtiles;
     unsigned long long N;
     const int* done_flag;
 };
@@ -389,6 +392,198 @@ __global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2, warp-pipelined.  Same three phases, but every WARP owns its own small tiles (<= kWHitCap hits,
+// <= kWRowCap rows), its own 2-stage shared-memory ring and its own mbarriers: a warp's lane 0 issues the
+// bulk-async copies of its next tile, the warp waits on its own barrier, phases are separated by
+// __syncwarp only.  There is no CTA-wide barrier anywhere in the main loop, so the latency one warp spends
+// waiting for its theta gathers or for the shared-memory chain of a row sum is filled by the other ~11
+// warps of the SM instead of being multiplied by a __syncthreads.
+// Phase B maps G = 32 / rows lanes to a row, chosen per tile at run time (lane = row for the typical 20-30
+// rows per tile, more lanes per row when rows are long).
+// ------------------------------------------------------------------------------------------------
+constexpr int kWWarps = 4;        // warps per CTA
+constexpr int kWStages = 2;
+constexpr int kWHitCap = 576;     // hits per warp tile
+constexpr int kWRowCap = 128;     // rows per warp tile
+
+struct __align__(16) WStage {
+    double con[kWHitCap + 4];
+    unsigned long long rp[kWRowCap + 4];
+    double ncp[kWRowCap + 4];
+    int sid[kWHitCap + 8];
+};
+static_assert(sizeof(WStage) % 16 == 0, "stage must keep 16 B alignment");
+
+struct WSmem {
+    WStage stage[kWWarps][kWStages];
+    unsigned long long full_bar[kWWarps][kWStages];
+    TileDesc desc[kWWarps][kWStages];
+    double red[kWWarps];
+};
+
+__device__ __forceinline__ void issue_wtile(const EstepArgs& a, unsigned k, WStage& st, unsigned long long* bar,
+                                            TileDesc& desc) {
+    const unsigned long long rs = a.wtile_row[k], re = a.wtile_row[k + 1];
+    const unsigned long long hs = a.wtile_hit[k], he = a.wtile_hit[k + 1];
+    desc.rs = rs;
+    desc.hs = hs;
+    desc.nr = (unsigned)(re - rs);
+    desc.nh = (unsigned)(he - hs);
+    const unsigned long long hs4 = hs & ~3ull, hs2 = hs & ~1ull, rs2 = rs & ~1ull;
+    const unsigned b_sid = round16((unsigned)(he - hs4) * 4u);
+    const unsigned b_con = round16((unsigned)(he - hs2) * 8u);
+    const unsigned b_rp = round16((unsigned)(re + 1 - rs2) * 8u);
+    const unsigned b_nc = round16((unsigned)(re - rs2) * 8u);
+    mbar_expect_tx(bar, b_sid + b_con + b_rp + b_nc);
+    if (b_sid) bulk_load(st.sid, a.sid + hs4, b_sid, bar);
+    if (b_con) bulk_load(st.con, a.conprb + hs2, b_con, bar);
+    bulk_load(st.rp, a.row_ptr + rs2, b_rp, bar);
+    bulk_load(st.ncp, a.ncpv + rs2, b_nc, bar);
+}
+
+template <bool WRITE_POST>
+__global__ void __launch_bounds__(kWWarps * 32, 3) estep_warp_kernel(const EstepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    WSmem& sm = *reinterpret_cast<WSmem*>(smem_raw);
+    if (*a.done_flag) return;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned n_streams = gridDim.x * kWWarps;          // one tile stream per warp
+    const unsigned stream = blockIdx.x * kWWarps + warp;
+    if (lane == 0) {
+        for (int s = 0; s < kWStages; ++s) mbar_init(&sm.full_bar[warp][s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (lane == 0) {
+        for (int s = 0; s < kWStages; ++s) {
+            const unsigned long long k = (unsigned long long)stream + (unsigned long long)s * n_streams;
+            if (k < a.n_wtiles) issue_wtile(a, (unsigned)k, sm.stage[warp][s], &sm.full_bar[warp][s], sm.desc[warp][s]);
+        }
+    }
+    __syncwarp();
+
+    constexpr int kPairs = 2;
+    const double theta0 = __ldg(a.theta);
+    double acc0 = 0.0;
+    unsigned it = 0;
+    for (unsigned long long k = stream; k < a.n_wtiles; k += n_streams, ++it) {
+        const int s = it % kWStages;
+        const unsigned parity = (it / kWStages) & 1u;
+        WStage& st = sm.stage[warp][s];
+        mbar_wait(&sm.full_bar[warp][s], parity);
+
+        const unsigned long long rs = sm.desc[warp][s].rs, hs = sm.desc[warp][s].hs;
+        const unsigned nr = sm.desc[warp][s].nr, nh = sm.desc[warp][s].nh;
+        const unsigned roff = (unsigned)(rs & 1ull);
+        const unsigned con_lead = (unsigned)(hs & 1ull);
+        const unsigned sid_shift = (unsigned)(hs & 2ull);
+        const unsigned n_pairs = (con_lead + nh + 1) >> 1;
+        double2* con2 = reinterpret_cast<double2*>(st.con);
+        const uint2* sid2 = reinterpret_cast<const uint2*>(st.sid + sid_shift);
+        double* s_con = st.con + con_lead;
+
+        // ---- phase A: products, flat over pairs of hits
+        for (unsigned p0 = lane; p0 < n_pairs; p0 += 32 * kPairs) {
+            uint2 t[kPairs];
+            double2 c[kPairs];
+            double th[2 * kPairs];
+#pragma unroll
+            for (int u = 0; u < kPairs; ++u) {
+                const unsigned p = p0 + 32 * u;
+                t[u] = p < n_pairs ? sid2[p] : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < kPairs; ++u) {
+                th[2 * u] = __ldg(a.theta + t[u].x);
+                th[2 * u + 1] = __ldg(a.theta + t[u].y);
+            }
+#pragma unroll
+            for (int u = 0; u < kPairs; ++u) {
+                const unsigned p = p0 + 32 * u;
+                c[u] = p < n_pairs ? con2[p] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < kPairs; ++u) {
+                const unsigned p = p0 + 32 * u;
+                double2 f;
+                f.x = th[2 * u] * c[u].x;
+                f.y = th[2 * u + 1] * c[u].y;
+                if (f.x < kEpsilon) f.x = 0.0;
+                if (f.y < kEpsilon) f.y = 0.0;
+                if (p < n_pairs) con2[p] = f;
+            }
+        }
+        __syncwarp();
+
+        // ---- phase B: row sums; G lanes per row, G = largest power of two <= 32 / min(nr, 32)
+        {
+            const unsigned rows_now = nr < 32u ? nr : 32u;
+            const unsigned shift = 31u - __clz(32u / rows_now);   // log2(G)
+            const unsigned G = 1u << shift;
+            const unsigned g = lane & (G - 1), row_in_pass = lane >> shift, rows_per_pass = 32u >> shift;
+            for (unsigned rb = 0; rb < nr; rb += rows_per_pass) {
+                const unsigned row = rb + row_in_pass;
+                const bool valid = row < nr;
+                unsigned b = 0, e = 0;
+                if (valid) {
+                    b = (unsigned)(st.rp[roff + row] - hs);
+                    e = (unsigned)(st.rp[roff + row + 1] - hs);
+                }
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, f0 = 0.0;
+                unsigned j = b + g;
+                const unsigned step = G;
+                for (; j + 3 * step < e; j += 4 * step) {
+                    s0 += s_con[j];
+                    s1 += s_con[j + step];
+                    s2 += s_con[j + 2 * step];
+                    s3 += s_con[j + 3 * step];
+                }
+                for (; j < e; j += step) s0 += s_con[j];
+                double part = (s0 + s1) + (s2 + s3);
+                if (valid && g == 0) {
+                    f0 = theta0 * st.ncp[roff + row];
+                    if (f0 < kEpsilon) f0 = 0.0;
+                    part += f0;
+                }
+                for (unsigned o = G >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                const double inv = part >= kEpsilon ? 1.0 / part : 0.0;
+                for (j = b + g; j < e; j += step) s_con[j] *= inv;
+                if (valid && g == 0) {
+                    const double p0 = f0 * inv;
+                    acc0 += p0;
+                    if (WRITE_POST) a.post0[rs + row] = p0;
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- phase C: count updates, flat over pairs of hits
+        for (unsigned p = lane; p < n_pairs; p += 32) {
+            const double2 w = con2[p];
+            const uint2 t = sid2[p];
+            const unsigned j0 = 2 * p - con_lead, j1 = j0 + 1;
+            if (j0 < nh) {
+                if (w.x != 0.0) red_add_f64(a.count + t.x, w.x);
+                if (WRITE_POST) a.post[hs + j0] = w.x;
+            }
+            if (j1 < nh) {
+                if (w.y != 0.0) red_add_f64(a.count + t.y, w.y);
+                if (WRITE_POST) a.post[hs + j1] = w.y;
+            }
+        }
+        fence_proxy_async();  // this warp's generic-proxy writes to the stage precede its next bulk-async fill
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned long long kn = k + (unsigned long long)kWStages * n_streams;
+            if (kn < a.n_wtiles) issue_wtile(a, (unsigned)kn, st, &sm.full_bar[warp][s], sm.desc[warp][s]);
+        }
+        __syncwarp();
+    }
+    flush_count0(acc0, sm.red, a.count);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2, direct variant: same row logic, loads straight from global memory (no staging).  Used as
 // the fallback for rows longer than a stage and as the comparison point in the profiles.
 // ------------------------------------------------------------------------------------------------
@@ -565,6 +760,19 @@ int launch_variant(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
 }
 
 template <bool WP>
+int launch_warp(rsem_b200_ctx* ctx, const EstepArgs& a) {
+    auto kern = estep_warp_kernel<WP>;
+    const size_t smem = sizeof(WSmem);
+    RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned long long want = ((unsigned long long)a.n_wtiles + kWWarps - 1) / kWWarps;
+    unsigned grid = (unsigned)std::min<unsigned long long>(want ? want : 1, (unsigned long long)ctx->sm_count * 3);
+    kern<<<grid, kWWarps * 32, smem, ctx->stream>>>(a);
+    RB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+template <bool WP>
 int launch_group(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
     if (tma) {
         switch (ctx->tma_group) {
@@ -615,34 +823,11 @@ int em_max_degree(rsem_b200_ctx* ctx, uint32_t* max_deg) {  // max_deg[0] = long
     return 0;
 }
 
-int em_build_tiles(rsem_b200_ctx* ctx) {
-    if (ctx->tile_row) { cudaFree(ctx->tile_row); ctx->tile_row = nullptr; }
-    if (ctx->tile_hit) { cudaFree(ctx->tile_hit); ctx->tile_hit = nullptr; }
-    ctx->n_tiles = 0;
-    if (ctx->N == 0) return 0;
-    RB_CUDA(cudaStreamSynchronize(ctx->stream));
-    uint32_t deg_info[2] = {0, 0};
-    if (int rc = em_max_degree(ctx, deg_info)) return rc;
-    ctx->max_deg = deg_info[0];
-
-    // lanes per row from the mean degree (+1 for the noise entry)
-    const double mean_deg = (double)ctx->H / (double)ctx->N + 1.0;
-    ctx->group = mean_deg <= 5.0 ? 4 : mean_deg <= 11.0 ? 8 : mean_deg <= 26.0 ? 16 : 32;
-    // lanes per row in phase B of the staged kernel: about one lane per 5 hits
-    ctx->tma_group = mean_deg <= 7.0 ? 1 : mean_deg <= 14.0 ? 2 : mean_deg <= 28.0 ? 4 : mean_deg <= 56.0 ? 8 : mean_deg <= 112.0 ? 16 : 32;
-    if (const char* e = getenv("RSEM_B200_GROUP")) {  // tuning knob (profiling only)
-        const int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ctx->tma_group = v;
-    }
-
-    // rows too long for a stage, or rows without hits (never produced by rsem-parse-alignments,
-    // HitContainer.h:67 asserts tot > 0): direct kernel only
-    if (ctx->max_deg > (uint32_t)kTileHitCap / 3 || deg_info[1]) return 0;
-    // hits per tile <= W + max_deg: keep that within one fully unrolled phase-A pass (4 hits per thread)
-    // when rows are short enough, otherwise within the stage capacity
-    unsigned long long W = ctx->max_deg <= 256 ? 4ull * kThreads - ctx->max_deg : (unsigned long long)kTileHitCap - ctx->max_deg;
-    // rows per tile <= W / C + 1 must fit the stage's row arrays; start from the byte-balanced weight
-    // (a row costs about as much traffic as a hit) and grow C only for matrices with very short rows
+// Cuts the rows into tiles of at most W + max_deg hits and at most row_cap rows: tile k holds the rows r with
+// row_ptr[r] + C * r in [k W, (k + 1) W).  C starts at the byte-balanced weight 1 (a row costs about as much
+// traffic as a hit) and doubles only for matrices whose rows are so short that row_cap would be exceeded.
+static int build_tile_set(rsem_b200_ctx* ctx, unsigned long long W, unsigned row_cap, uint64_t** out_row,
+                          uint64_t** out_hit, uint32_t* out_n) {
     unsigned long long C = 1, n_raw = 0;
     unsigned long long* raw = nullptr;
     for (;;) {
@@ -662,7 +847,7 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
         RB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         RB_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(d_max);
-        if (h_max <= (unsigned)kTileRowCap) break;
+        if (h_max <= row_cap) break;
         cudaFree(raw);
         raw = nullptr;
         C *= 2;
@@ -672,19 +857,57 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
     auto end = thrust::unique(thrust::cuda::par.on(ctx->stream), p, p + n_raw + 1);
     const unsigned long long n_bounds = (unsigned long long)(end - p);
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (n_bounds < 2) { cudaFree(raw); return 0; }
-    ctx->n_tiles = (uint32_t)(n_bounds - 1);
-    RB_CUDA(cudaMalloc(&ctx->tile_row, n_bounds * sizeof(uint64_t)));
-    RB_CUDA(cudaMalloc(&ctx->tile_hit, n_bounds * sizeof(uint64_t)));
-    RB_CUDA(cudaMemcpyAsync(ctx->tile_row, raw, n_bounds * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (n_bounds < 2) { cudaFree(raw); *out_n = 0; return 0; }
+    *out_n = (uint32_t)(n_bounds - 1);
+    RB_CUDA(cudaMalloc(out_row, n_bounds * sizeof(uint64_t)));
+    RB_CUDA(cudaMalloc(out_hit, n_bounds * sizeof(uint64_t)));
+    RB_CUDA(cudaMemcpyAsync(*out_row, raw, n_bounds * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
     gather_u64_kernel<<<(unsigned)((n_bounds + 255) / 256), 256, 0, ctx->stream>>>(
-        reinterpret_cast<const unsigned long long*>(ctx->row_ptr),
-        reinterpret_cast<const unsigned long long*>(ctx->tile_row), n_bounds,
-        reinterpret_cast<unsigned long long*>(ctx->tile_hit));
+        reinterpret_cast<const unsigned long long*>(ctx->row_ptr), reinterpret_cast<const unsigned long long*>(*out_row),
+        n_bounds, reinterpret_cast<unsigned long long*>(*out_hit));
     RB_CUDA(cudaGetLastError());
     ctx->launches++;
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(raw);
+    return 0;
+}
+
+int em_build_tiles(rsem_b200_ctx* ctx) {
+    if (ctx->tile_row) { cudaFree(ctx->tile_row); ctx->tile_row = nullptr; }
+    if (ctx->tile_hit) { cudaFree(ctx->tile_hit); ctx->tile_hit = nullptr; }
+    if (ctx->wtile_row) { cudaFree(ctx->wtile_row); ctx->wtile_row = nullptr; }
+    if (ctx->wtile_hit) { cudaFree(ctx->wtile_hit); ctx->wtile_hit = nullptr; }
+    ctx->n_tiles = ctx->n_wtiles = 0;
+    if (ctx->N == 0) return 0;
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint32_t deg_info[2] = {0, 0};
+    if (int rc = em_max_degree(ctx, deg_info)) return rc;
+    ctx->max_deg = deg_info[0];
+
+    // lanes per row from the mean degree (+1 for the noise entry)
+    const double mean_deg = (double)ctx->H / (double)ctx->N + 1.0;
+    ctx->group = mean_deg <= 5.0 ? 4 : mean_deg <= 11.0 ? 8 : mean_deg <= 26.0 ? 16 : 32;
+    // lanes per row in phase B of the CTA-staged kernel: about one lane per 5 hits
+    ctx->tma_group = mean_deg <= 7.0 ? 1 : mean_deg <= 14.0 ? 2 : mean_deg <= 28.0 ? 4 : mean_deg <= 56.0 ? 8 : mean_deg <= 112.0 ? 16 : 32;
+    if (const char* e = getenv("RSEM_B200_GROUP")) {  // tuning knob (profiling only)
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ctx->tma_group = v;
+    }
+    // rows without hits are never produced by rsem-parse-alignments (HitContainer.h:67 asserts tot > 0): the
+    // staged kernels do not handle them, the direct kernel does
+    if (deg_info[1]) return 0;
+
+    // CTA tiles: hits <= W + max_deg, kept within one fully unrolled phase-A pass (4 hits per thread) when rows
+    // are short enough, otherwise within the stage capacity
+    if (ctx->max_deg <= (uint32_t)kTileHitCap / 3) {
+        const unsigned long long W = ctx->max_deg <= 256 ? 4ull * kThreads - ctx->max_deg : (unsigned long long)kTileHitCap - ctx->max_deg;
+        if (int rc = build_tile_set(ctx, W, kTileRowCap, &ctx->tile_row, &ctx->tile_hit, &ctx->n_tiles)) return rc;
+    }
+    // warp tiles
+    if (ctx->max_deg <= (uint32_t)kWHitCap / 2) {
+        const unsigned long long W = (unsigned long long)kWHitCap - ctx->max_deg;
+        if (int rc = build_tile_set(ctx, W, kWRowCap, &ctx->wtile_row, &ctx->wtile_hit, &ctx->n_wtiles)) return rc;
+    }
     return 0;
 }
 
@@ -701,12 +924,18 @@ int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
     a.tile_row = reinterpret_cast<const unsigned long long*>(ctx->tile_row);
     a.tile_hit = reinterpret_cast<const unsigned long long*>(ctx->tile_hit);
     a.n_tiles = ctx->n_tiles;
+    a.wtile_row = reinterpret_cast<const unsigned long long*>(ctx->wtile_row);
+    a.wtile_hit = reinterpret_cast<const unsigned long long*>(ctx->wtile_hit);
+    a.n_wtiles = ctx->n_wtiles;
     a.N = ctx->N;
     a.done_flag = ctx->done_flag;
     if (ctx->N == 0) return 0;
-    bool tma = ctx->n_tiles > 0 && ctx->variant != 2;
-    if (ctx->variant == 1 && ctx->n_tiles == 0) {
-        set_error("TMA-staged E-step requested but rows are too long for a stage");
+    // variant: 0 auto (CTA-staged > warp-pipelined > direct; measured on C3: 5.9 / 6.4 / 9.3 ms), 1 CTA-staged,
+    // 2 direct, 3 warp-pipelined
+    const bool use_warp = ctx->n_wtiles > 0 && (ctx->variant == 3 || (ctx->variant == 0 && ctx->n_tiles == 0));
+    const bool tma = !use_warp && ctx->n_tiles > 0 && ctx->variant != 2 && ctx->variant != 3;
+    if ((ctx->variant == 1 && ctx->n_tiles == 0) || (ctx->variant == 3 && ctx->n_wtiles == 0)) {
+        set_error("staged E-step requested but the matrix has rows that are empty or too long for a stage");
         return RSEM_B200_ERR_UNSUPPORTED;
     }
 
@@ -723,7 +952,9 @@ int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
         ctx->ev_used++;
         RB_CUDA(cudaEventRecord(e0, ctx->stream));
     }
-    int rc = write_post ? launch_group<true>(ctx, a, tma) : launch_group<false>(ctx, a, tma);
+    int rc;
+    if (use_warp) rc = write_post ? launch_warp<true>(ctx, a) : launch_warp<false>(ctx, a);
+    else rc = write_post ? launch_group<true>(ctx, a, tma) : launch_group<false>(ctx, a, tma);
     if (rc) return rc;
     if (ctx->profiling) RB_CUDA(cudaEventRecord(e1, ctx->stream));
     return 0;
