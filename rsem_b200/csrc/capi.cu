@@ -42,6 +42,7 @@ void free_hits(rsem_b200_ctx* c) {
     if (c->count) dev_free(c, &c->count, (size_t)c->M + 1);
     if (c->tile_row) { cudaFree(c->tile_row); c->tile_row = nullptr; }
     if (c->tile_hit) { cudaFree(c->tile_hit); c->tile_hit = nullptr; }
+    if (c->tile_meta) { cudaFree(c->tile_meta); c->tile_meta = nullptr; }
     if (c->wtile_row) { cudaFree(c->wtile_row); c->wtile_row = nullptr; }
     if (c->wtile_hit) { cudaFree(c->wtile_hit); c->wtile_hit = nullptr; }
     c->n_tiles = c->n_wtiles = 0;

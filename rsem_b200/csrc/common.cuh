@@ -124,6 +124,7 @@ struct rsem_b200_ctx {
     // E-step tiling (em_kernels.cu)
     uint64_t* tile_row = nullptr;
     uint64_t* tile_hit = nullptr;
+    void* tile_meta = nullptr;      // per-tile head masks (em_kernels.cu TileMeta)
     uint32_t n_tiles = 0;
     uint64_t* wtile_row = nullptr;  // warp-pipelined kernel's own (smaller) tiles
     uint64_t* wtile_hit = nullptr;

@@ -36,17 +36,28 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 constexpr int kThreads = 512;
 constexpr int kStages = 3;
-constexpr int kTileHitCap = 2304;  // max hits a stage can hold
+constexpr int kTileHitCap = 2048;  // max hits a stage can hold (actual tiles hold <= 2046: 1024 16-byte pairs)
 constexpr int kTileRowCap = 512;   // max rows a stage can hold (kThreads / G for the actual G)
 constexpr int kSidElems = kTileHitCap + 8;
 constexpr int kConElems = kTileHitCap + 4;
 constexpr int kRowElems = kTileRowCap + 4;
+
+// Static per-tile metadata, built once per upload and streamed with the tile: bit q of `mask` is set iff
+// element q of the tile's pair space (q = tile-local hit index + (first hit index & 1)) starts a row;
+// pre[w] = number of set bits in mask words < w.  row(q) = pre[q / 32] + popc(mask[q / 32] & bits(0..q % 32)) - 1.
+constexpr int kMaskWords = 68;
+struct __align__(16) TileMeta {
+    unsigned mask[kMaskWords];
+    unsigned short pre[kMaskWords + 4];
+};
+static_assert(sizeof(TileMeta) % 16 == 0, "tile metadata must keep 16 B alignment");
 
 struct __align__(16) Stage {
     double con[kConElems];
     unsigned long long rp[kRowElems];
     double ncp[kRowElems];
     int sid[kSidElems];
+    TileMeta meta;
 };
 static_assert(sizeof(Stage) % 16 == 0, "stage must keep 16 B alignment");
 
@@ -60,6 +71,7 @@ struct SmemLayout {
     unsigned long long full_bar[kStages];
     TileDesc desc[kStages];
     double red[kThreads / 32];
+    double inv[kTileRowCap];  // 1 / row sum of the tile being processed
 };
 
 struct EstepArgs {
@@ -73,6 +85,7 @@ struct EstepArgs {
     double* post0;
     const unsigned long long* tile_row;
     const unsigned long long* tile_hit;
+    const void* tile_meta;
     unsigned int n_tiles;
     const unsigned long long* wtile_row;
     const unsigned long long* wtile_hit;
@@ -225,11 +238,12 @@ __device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage
     const unsigned b_con = round16((unsigned)(he - hs2) * 8u);
     const unsigned b_rp = round16((unsigned)(re + 1 - rs2) * 8u);
     const unsigned b_nc = round16((unsigned)(re - rs2) * 8u);
-    mbar_expect_tx(bar, b_sid + b_con + b_rp + b_nc);
+    mbar_expect_tx(bar, b_sid + b_con + b_rp + b_nc + (unsigned)sizeof(TileMeta));
     if (b_sid) bulk_load(st.sid, a.sid + hs4, b_sid, bar);
     if (b_con) bulk_load(st.con, a.conprb + hs2, b_con, bar);
     bulk_load(st.rp, a.row_ptr + rs2, b_rp, bar);
     bulk_load(st.ncp, a.ncpv + rs2, b_nc, bar);
+    bulk_load(&st.meta, static_cast<const TileMeta*>(a.tile_meta) + k, (unsigned)sizeof(TileMeta), bar);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -294,14 +308,17 @@ __global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs 
         const uint2* sid2 = reinterpret_cast<const uint2*>(st.sid + sid_shift);
         double* s_con = st.con + con_lead;  // element 0 = first hit of the tile (phase B)
 
-        // ---- phase A
-        for (unsigned p0 = tid; p0 < n_pairs; p0 += kThreads * kPairs) {
-            uint2 t[kPairs];
+        // ---- phase A: products for this thread's two pairs; they stay in registers for phase C and are
+        //      also written over the conprb slots for the row sums of phase B.  (The tile builder keeps
+        //      n_pairs <= kThreads * kPairs, so one pass covers the tile.)
+        uint2 t[kPairs];
+        double2 f[kPairs];
+        {
             double2 c[kPairs];
             double th[2 * kPairs];
 #pragma unroll
             for (int u = 0; u < kPairs; ++u) {
-                const unsigned p = p0 + kThreads * u;
+                const unsigned p = tid + kThreads * u;
                 t[u] = p < n_pairs ? sid2[p] : make_uint2(0u, 0u);
             }
 #pragma unroll
@@ -311,23 +328,23 @@ __global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs 
             }
 #pragma unroll
             for (int u = 0; u < kPairs; ++u) {
-                const unsigned p = p0 + kThreads * u;
+                const unsigned p = tid + kThreads * u;
                 c[u] = p < n_pairs ? con2[p] : make_double2(0.0, 0.0);
             }
 #pragma unroll
             for (int u = 0; u < kPairs; ++u) {
-                const unsigned p = p0 + kThreads * u;
-                double2 f;
-                f.x = th[2 * u] * c[u].x;
-                f.y = th[2 * u + 1] * c[u].y;
-                if (f.x < kEpsilon) f.x = 0.0;
-                if (f.y < kEpsilon) f.y = 0.0;
-                if (p < n_pairs) con2[p] = f;
+                const unsigned p = tid + kThreads * u;
+                f[u].x = th[2 * u] * c[u].x;
+                f[u].y = th[2 * u + 1] * c[u].y;
+                if (f[u].x < kEpsilon) f[u].x = 0.0;
+                if (f[u].y < kEpsilon) f[u].y = 0.0;
+                if (p < n_pairs) con2[p] = f[u];
             }
         }
         __syncthreads();
 
-        // ---- phase B (one pass when the tile has <= kThreads / G rows, which the tile builder aims for)
+        // ---- phase B: 1 / (noise term + row sum) per row (one pass when the tile has <= kThreads / G rows,
+        //      which the tile builder aims for)
         for (unsigned rbase = 0; rbase < nr; rbase += kThreads / G) {
             const unsigned row = rbase + row_in_tile;
             const bool valid = row < nr;
@@ -351,14 +368,9 @@ __global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs 
                 part += f0;
             }
             const double sum = group_sum<G>(part);
-            const double inv = sum >= kEpsilon ? 1.0 / sum : 0.0;
-#pragma unroll
-            for (int q = 0; q < kSlots; ++q) {
-                const unsigned j = b + g + q * G;
-                if (j < e) s_con[j] = x[q] * inv;
-            }
-            for (unsigned j = b + g + kSlots * G; j < e; j += G) s_con[j] *= inv;
             if (valid && g == 0) {
+                const double inv = sum >= kEpsilon ? 1.0 / sum : 0.0;
+                sm.inv[row] = inv;
                 const double p0 = f0 * inv;
                 acc0 += p0;
                 if (WRITE_POST) a.post0[rs + row] = p0;
@@ -366,19 +378,25 @@ __global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs 
         }
         __syncthreads();
 
-        // ---- phase C
-        for (unsigned p = tid; p < n_pairs; p += kThreads) {
-            const double2 w = con2[p];
-            const uint2 t = sid2[p];
-            const unsigned j0 = 2 * p - con_lead;  // tile-local hit index of w.x (wraps for the lead-in element)
+        // ---- phase C: weight = product (register) * inv[row]; the row of an element comes from the static head
+        //      mask: row(q) = pre[q / 32] + popc(mask[q / 32] & bits(0 .. q % 32)) - 1
+#pragma unroll
+        for (int u = 0; u < kPairs; ++u) {
+            const unsigned p = tid + kThreads * u;
+            const unsigned j0 = 2 * p - con_lead, j1 = j0 + 1;  // tile-local hit indices (j0 wraps for a lead-in element)
+            const unsigned word = st.meta.mask[p >> 4];
+            const unsigned bx = (p & 15u) << 1;
+            const unsigned rx = (unsigned)st.meta.pre[p >> 4] + __popc(word & (0xffffffffu >> (31u - bx))) - 1u;
+            const unsigned ry = rx + ((word >> (bx + 1u)) & 1u);
             if (j0 < nh) {
-                if (w.x != 0.0) red_add_f64(a.count + t.x, w.x);
-                if (WRITE_POST) a.post[hs + j0] = w.x;
+                const double w = f[u].x * sm.inv[rx];
+                if (w != 0.0) red_add_f64(a.count + t[u].x, w);
+                if (WRITE_POST) a.post[hs + j0] = w;
             }
-            const unsigned j1 = j0 + 1;  // 0 for the lead-in pair
             if (j1 < nh) {
-                if (w.y != 0.0) red_add_f64(a.count + t.y, w.y);
-                if (WRITE_POST) a.post[hs + j1] = w.y;
+                const double w = f[u].y * sm.inv[ry];
+                if (w != 0.0) red_add_f64(a.count + t[u].y, w);
+                if (WRITE_POST) a.post[hs + j1] = w;
             }
         }
         fence_proxy_async();  // generic-proxy writes to the stage precede its next bulk-async fill
@@ -638,6 +656,31 @@ __global__ void tile_bounds_kernel(const unsigned long long* row_ptr, unsigned l
     tile_row[k] = lo;
 }
 
+// one block per tile: head-bit mask over the tile's pair space + prefix popcounts (TileMeta)
+__global__ void tile_meta_kernel(const unsigned long long* row_ptr, const unsigned long long* tile_row,
+                                 const unsigned long long* tile_hit, TileMeta* out) {
+    __shared__ unsigned m[kMaskWords];
+    const unsigned k = blockIdx.x;
+    for (int w = threadIdx.x; w < kMaskWords; w += blockDim.x) m[w] = 0u;
+    __syncthreads();
+    const unsigned long long rs = tile_row[k], re = tile_row[k + 1], hs = tile_hit[k];
+    const unsigned lead = (unsigned)(hs & 1ull);
+    for (unsigned long long r = rs + threadIdx.x; r < re; r += blockDim.x) {
+        const unsigned q = (unsigned)(row_ptr[r] - hs) + lead;
+        atomicOr(&m[q >> 5], 1u << (q & 31u));
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < kMaskWords; w += blockDim.x) out[k].mask[w] = m[w];
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int w = 0; w < kMaskWords; ++w) {
+            out[k].pre[w] = (unsigned short)run;
+            run += __popc(m[w]);
+        }
+        for (int w = kMaskWords; w < kMaskWords + 4; ++w) out[k].pre[w] = (unsigned short)run;
+    }
+}
+
 __global__ void max_diff_kernel(const unsigned long long* v, unsigned long long n, unsigned int* out) {
     unsigned int m = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -875,6 +918,7 @@ static int build_tile_set(rsem_b200_ctx* ctx, unsigned long long W, unsigned row
 int em_build_tiles(rsem_b200_ctx* ctx) {
     if (ctx->tile_row) { cudaFree(ctx->tile_row); ctx->tile_row = nullptr; }
     if (ctx->tile_hit) { cudaFree(ctx->tile_hit); ctx->tile_hit = nullptr; }
+    if (ctx->tile_meta) { cudaFree(ctx->tile_meta); ctx->tile_meta = nullptr; }
     if (ctx->wtile_row) { cudaFree(ctx->wtile_row); ctx->wtile_row = nullptr; }
     if (ctx->wtile_hit) { cudaFree(ctx->wtile_hit); ctx->wtile_hit = nullptr; }
     ctx->n_tiles = ctx->n_wtiles = 0;
@@ -899,9 +943,20 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
 
     // CTA tiles: hits <= W + max_deg, kept within one fully unrolled phase-A pass (4 hits per thread) when rows
     // are short enough, otherwise within the stage capacity
-    if (ctx->max_deg <= (uint32_t)kTileHitCap / 3) {
-        const unsigned long long W = ctx->max_deg <= 256 ? 4ull * kThreads - ctx->max_deg : (unsigned long long)kTileHitCap - ctx->max_deg;
+    if (ctx->max_deg <= (uint32_t)kTileHitCap / 4) {
+        // hits <= W + max_deg <= 2046, so that the pair space (<= 1 lead-in element + hits, rounded up) has at most
+        // kThreads * 2 pairs: every thread owns exactly two pairs of a tile
+        const unsigned long long W = 4ull * kThreads - 2 - ctx->max_deg;
         if (int rc = build_tile_set(ctx, W, kTileRowCap, &ctx->tile_row, &ctx->tile_hit, &ctx->n_tiles)) return rc;
+        if (ctx->n_tiles > 0) {
+            RB_CUDA(cudaMalloc(&ctx->tile_meta, (size_t)ctx->n_tiles * sizeof(TileMeta)));
+            tile_meta_kernel<<<ctx->n_tiles, 64, 0, ctx->stream>>>(
+                reinterpret_cast<const unsigned long long*>(ctx->row_ptr), reinterpret_cast<const unsigned long long*>(ctx->tile_row),
+                reinterpret_cast<const unsigned long long*>(ctx->tile_hit), static_cast<TileMeta*>(ctx->tile_meta));
+            RB_CUDA(cudaGetLastError());
+            ctx->launches++;
+            RB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
     }
     // warp tiles
     if (ctx->max_deg <= (uint32_t)kWHitCap / 2) {
@@ -923,6 +978,7 @@ int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
     a.post0 = ctx->post0;
     a.tile_row = reinterpret_cast<const unsigned long long*>(ctx->tile_row);
     a.tile_hit = reinterpret_cast<const unsigned long long*>(ctx->tile_hit);
+    a.tile_meta = ctx->tile_meta;
     a.n_tiles = ctx->n_tiles;
     a.wtile_row = reinterpret_cast<const unsigned long long*>(ctx->wtile_row);
     a.wtile_hit = reinterpret_cast<const unsigned long long*>(ctx->wtile_hit);
