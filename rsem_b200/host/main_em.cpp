@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <future>
 
 #include "host.hpp"
 
@@ -53,7 +54,10 @@ int env_int(const char* name, int dflt) {
 }
 
 void print_round(int round, const rsem_b200_round_stats& s) {
-    if (g_verbose) printf("ROUND = %d, SUM = %.15g, bChange = %.6g, totNum = %lld\n", round, s.sum, s.bchange, (long long)s.totnum);
+    if (g_verbose) {  // the reference ends the line with std::endl, i.e. flushes it (EM.cpp:415); harnesses timestamp these lines
+        printf("ROUND = %d, SUM = %.15g, bChange = %.6g, totNum = %lld\n", round, s.sum, s.bchange, (long long)s.totnum);
+        fflush(stdout);
+    }
 }
 
 // imd.ofg, EM.cpp:435-457: "M N0" then one line per read with >= 1 surviving entry
@@ -99,6 +103,15 @@ int main(int argc, char* argv[]) {
     if (a.read_type < 0 || a.read_type > 3) { fprintf(stderr, "Unknown Read Type!\n"); exit(-1); }
     if (a.genBam)
         die("rsem-run-em (B200): -b (posterior BAM output) is not implemented; run rsem-calculate-expression with --no-bam-output.");
+
+    // CUDA context creation takes seconds on a multi-GPU node: start it now, overlap it with the file parsing
+    struct CtxResult { int rc; rsem_b200_ctx* ctx; std::string err; };
+    std::future<CtxResult> ctx_future = std::async(std::launch::async, []() {
+        CtxResult r{0, nullptr, ""};
+        r.rc = rsem_b200_ctx_create(env_int("RSEM_B200_DEVICE", 0), &r.ctx);
+        if (r.rc != 0) r.err = rsem_b200_last_error();  // the message is thread-local: take it here
+        return r;
+    });
 
     RefData refs;
     load_refs(a.refName + ".seq", true, refs);
@@ -159,7 +172,11 @@ int main(int argc, char* argv[]) {
 
     // ---- device set-up ----
     rsem_b200_ctx* ctx = nullptr;
-    check_rc(rsem_b200_ctx_create(env_int("RSEM_B200_DEVICE", 0), &ctx), "ctx_create");
+    {
+        CtxResult r = ctx_future.get();
+        if (r.rc != 0) die("rsem_b200: ctx_create failed: " + r.err);
+        ctx = r.ctx;
+    }
     check_rc(rsem_b200_upload_hits(ctx, hits.N, hits.H, M, hits.row_ptr.data(), hits.sid.data(), hits.pos.data(),
                                    a.read_type >= 2 ? hits.insertL.data() : nullptr), "upload_hits");
     check_rc(rsem_b200_upload_reads(ctx, reads.n_mates, reads.off[0].data(), reads.base[0].data(),
