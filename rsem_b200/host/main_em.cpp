@@ -6,7 +6,9 @@
 //
 // Differences from the reference, all outside the results:
 //   * -p is accepted and ignored for the EM (the result of the reference does not depend on it);
-//     the GPU is chosen with RSEM_B200_DEVICE (default 0).
+//     the GPU is chosen with RSEM_B200_DEVICE (default 0), several GPUs with RSEM_B200_DEVICES=0,1,..:
+//     reads are sharded over them like the reference shards them over threads, counts and model
+//     statistics are summed with ncclAllReduce.
 //   * -b (posterior BAM output) is not implemented yet: the run stops with an
 //     error before doing any work, so the Perl driver must be called with --no-bam-output.
 //   * RSEM_MAX_ROUND / RSEM_MIN_ROUND override the compile-time constants MAX_ROUND = 10000 and
@@ -17,6 +19,7 @@
 #include <cstring>
 #include <ctime>
 #include <future>
+#include <thread>
 
 #include "host.hpp"
 
@@ -58,6 +61,27 @@ void print_round(int round, const rsem_b200_round_stats& s) {
         printf("ROUND = %d, SUM = %.15g, bChange = %.6g, totNum = %lld\n", round, s.sum, s.bchange, (long long)s.totnum);
         fflush(stdout);
     }
+}
+
+// Contiguous read ranges with about nHits / world hits each: the greedy rule the reference uses for its threads
+// (EM.cpp:135-157; same as rsem_b200/sharding.py, tested against the reference's own "Thread i : N = .." lines).
+std::vector<std::pair<uint64_t, uint64_t>> shard_reads(const std::vector<uint64_t>& row_ptr, int world) {
+    const uint64_t n = row_ptr.size() - 1, thr = row_ptr[n] / (uint64_t)world;
+    std::vector<std::pair<uint64_t, uint64_t>> out;
+    uint64_t cur = 0;
+    for (int i = 0; i < world; ++i) {
+        const uint64_t left = (uint64_t)(world - i - 1);
+        uint64_t end = n;
+        if (i != world - 1) {
+            const uint64_t target = row_ptr[cur] + thr;
+            end = (uint64_t)(std::lower_bound(row_ptr.begin(), row_ptr.end(), target) - row_ptr.begin());
+            if (end < cur) end = cur;
+            if (end > n - left) end = n - left;
+        }
+        out.emplace_back(cur, end);
+        cur = end;
+    }
+    return out;
 }
 
 // imd.ofg, EM.cpp:435-457: "M N0" then one line per read with >= 1 surviving entry
@@ -170,88 +194,138 @@ int main(int argc, char* argv[]) {
     model.estimate_from_reads(a.imdName, reads);
     if (reads.n != N1) die("Read indices files do not match!");
 
-    // ---- device set-up ----
-    rsem_b200_ctx* ctx = nullptr;
+    // ---- device set-up: one worker (host thread + context) per GPU, reads sharded like the reference's threads ----
+    std::vector<int> devices;
+    if (const char* e = getenv("RSEM_B200_DEVICES")) {  // e.g. "0,1,2,3"
+        for (const char* q = e; *q;) {
+            devices.push_back(atoi(q));
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+    }
+    if (devices.size() <= 1) devices.assign(1, env_int("RSEM_B200_DEVICE", devices.empty() ? 0 : devices[0]));
+    if ((uint64_t)devices.size() > N1) devices.resize((size_t)N1);
+    const int world = (int)devices.size();
+    std::vector<std::pair<uint64_t, uint64_t>> shards = shard_reads(hits.row_ptr, world);
+    if (g_verbose && world > 1)
+        for (int r = 0; r < world; ++r)
+            printf("GPU %d : N = %llu, NHit = %llu\n", devices[r], (unsigned long long)(shards[r].second - shards[r].first),
+                   (unsigned long long)(hits.row_ptr[shards[r].second] - hits.row_ptr[shards[r].first]));
+
+    unsigned char uid[RSEM_B200_UNIQUE_ID_BYTES] = {0};
+    rsem_b200_ctx* ctx0 = nullptr;
     {
         CtxResult r = ctx_future.get();
         if (r.rc != 0) die("rsem_b200: ctx_create failed: " + r.err);
-        ctx = r.ctx;
+        ctx0 = r.ctx;
     }
-    check_rc(rsem_b200_upload_hits(ctx, hits.N, hits.H, M, hits.row_ptr.data(), hits.sid.data(), hits.pos.data(),
-                                   a.read_type >= 2 ? hits.insertL.data() : nullptr), "upload_hits");
-    check_rc(rsem_b200_upload_reads(ctx, reads.n_mates, reads.off[0].data(), reads.base[0].data(),
-                                    reads.has_qual ? reads.qual[0].data() : nullptr,
-                                    reads.n_mates == 2 ? reads.off[1].data() : nullptr,
-                                    reads.n_mates == 2 ? reads.base[1].data() : nullptr,
-                                    (reads.n_mates == 2 && reads.has_qual) ? reads.qual[1].data() : nullptr,
-                                    reads.lowq.data()), "upload_reads");
-    check_rc(rsem_b200_upload_refs(ctx, M, refs.seq_off.data(), refs.seq.data(), refs.full_len.data(), refs.tot_len.data(),
-                                   refs.mask_off.data(), refs.mask_words.data()), "upload_refs");
-    check_rc(rsem_b200_set_theta(ctx, theta.data()), "set_theta");
+    if (world > 1) check_rc(rsem_b200_comm_unique_id(uid), "comm_unique_id");
 
-    // ---- EM loop (EM.cpp:364-416) ----
-    std::vector<double> st_prof(model.n_prof()), st_noise(model.n_noise()), st_gld(mp.maxL - (mp.minL - 1) + 1), st_rspd(mp.B + 2);
-    rsem_b200_model_stats mstats;
-    mstats.profile = st_prof.data();
-    mstats.noise_profile = st_noise.data();
-    mstats.gld_pdf = st_gld.data();
-    mstats.gld_lb = mp.minL - 1;
-    mstats.gld_span = mp.maxL - (mp.minL - 1);
-    mstats.rspd_pdf = st_rspd.data();
-
-    bool model_dirty = true;  // device copy of the model tables / conprb is stale (needCalcConPrb)
-    auto push_model = [&]() {
-        rsem_b200_model abi;
-        model.fill_abi(abi);
-        check_rc(rsem_b200_set_model(ctx, &abi), "set_model");
-    };
-    int ROUND = 0;
+    std::vector<double> conprb(hits.H), ncpv(hits.N), counts(M + 1, 0.0);
+    HostModel final_model;
     long long totNum = 0;
-    const int CHUNK = 32;
-    std::vector<rsem_b200_round_stats> chunk_stats(CHUNK);
-    bool keep_going = true;
-    while (keep_going) {
-        ++ROUND;
-        if (ROUND <= 10) {  // doesUpdateModel, EM.cpp:307-310
-            if (model_dirty) { push_model(); model_dirty = false; }
-            rsem_b200_round_stats rs;
-            check_rc(rsem_b200_em_model_round(ctx, (double)N0, &mstats, &rs), "em_model_round");
-            model.rebuild(mstats);  // model.init(); collect(); finish()
-            model_dirty = true;
-            print_round(ROUND, rs);
-            totNum = rs.totnum;
-            keep_going = ROUND < MIN_ROUND || (totNum > 0 && ROUND < MAX_ROUND);
-        } else {
-            if (model_dirty) {
-                push_model();
-                check_rc(rsem_b200_calc_conprb(ctx), "calc_conprb");
-                model_dirty = false;
-            }
-            int32_t ran = 0, stopped = 0;
-            check_rc(rsem_b200_em_rounds(ctx, ROUND, CHUNK, MIN_ROUND, MAX_ROUND, (double)N0, chunk_stats.data(), &ran, &stopped), "em_rounds");
-            for (int r = 0; r < ran; ++r) print_round(ROUND + r, chunk_stats[r]);
-            if (ran > 0) { ROUND += ran - 1; totNum = chunk_stats[ran - 1].totnum; }
-            keep_going = !stopped;
+
+    auto worker = [&](int rank) {
+        rsem_b200_ctx* ctx = rank == 0 ? ctx0 : nullptr;
+        if (rank != 0) check_rc(rsem_b200_ctx_create(devices[rank], &ctx), "ctx_create");
+        if (world > 1) check_rc(rsem_b200_comm_init(ctx, uid, world, rank), "comm_init");
+        const uint64_t r0 = shards[rank].first, r1 = shards[rank].second;
+        const uint64_t h0 = hits.row_ptr[r0], h1 = hits.row_ptr[r1];
+        // shard-local CSR and read offsets (rebased to 0)
+        std::vector<uint64_t> rp(r1 - r0 + 1), off[2];
+        for (uint64_t i = r0; i <= r1; ++i) rp[i - r0] = hits.row_ptr[i] - h0;
+        for (int m = 0; m < reads.n_mates; ++m) {
+            off[m].resize(r1 - r0 + 1);
+            for (uint64_t i = r0; i <= r1; ++i) off[m][i - r0] = reads.off[m][i] - reads.off[m][r0];
         }
+        check_rc(rsem_b200_upload_hits(ctx, r1 - r0, h1 - h0, M, rp.data(), hits.sid.data() + h0, hits.pos.data() + h0,
+                                       a.read_type >= 2 ? hits.insertL.data() + h0 : nullptr), "upload_hits");
+        auto mate = [&](const std::vector<uint8_t>& v, int m) { return v.data() + reads.off[m][r0]; };
+        check_rc(rsem_b200_upload_reads(ctx, reads.n_mates, off[0].data(), mate(reads.base[0], 0),
+                                        reads.has_qual ? mate(reads.qual[0], 0) : nullptr,
+                                        reads.n_mates == 2 ? off[1].data() : nullptr,
+                                        reads.n_mates == 2 ? mate(reads.base[1], 1) : nullptr,
+                                        (reads.n_mates == 2 && reads.has_qual) ? mate(reads.qual[1], 1) : nullptr,
+                                        reads.lowq.data() + r0), "upload_reads");
+        check_rc(rsem_b200_upload_refs(ctx, M, refs.seq_off.data(), refs.seq.data(), refs.full_len.data(), refs.tot_len.data(),
+                                       refs.mask_off.data(), refs.mask_words.data()), "upload_refs");
+        check_rc(rsem_b200_set_theta(ctx, theta.data()), "set_theta");
+
+        // ---- EM loop (EM.cpp:364-416).  Every rank keeps its own copy of the master model and rebuilds it from the
+        // (allreduced, hence identical) statistics: no broadcast is needed.
+        HostModel mdl = model;
+        std::vector<double> st_prof(mdl.n_prof()), st_noise(mdl.n_noise()), st_gld(mp.maxL - (mp.minL - 1) + 1), st_rspd(mp.B + 2);
+        rsem_b200_model_stats mstats;
+        mstats.profile = st_prof.data();
+        mstats.noise_profile = st_noise.data();
+        mstats.gld_pdf = st_gld.data();
+        mstats.gld_lb = mp.minL - 1;
+        mstats.gld_span = mp.maxL - (mp.minL - 1);
+        mstats.rspd_pdf = st_rspd.data();
+
+        bool model_dirty = true;  // device copy of the model tables / conprb is stale (needCalcConPrb)
+        auto push_model = [&]() {
+            rsem_b200_model abi;
+            mdl.fill_abi(abi);
+            check_rc(rsem_b200_set_model(ctx, &abi), "set_model");
+        };
+        int ROUND = 0;
+        long long tot = 0;
+        const int CHUNK = 32;
+        std::vector<rsem_b200_round_stats> chunk_stats(CHUNK);
+        bool keep_going = true;
+        while (keep_going) {
+            ++ROUND;
+            if (ROUND <= 10) {  // doesUpdateModel, EM.cpp:307-310
+                if (model_dirty) { push_model(); model_dirty = false; }
+                rsem_b200_round_stats rs;
+                check_rc(rsem_b200_em_model_round(ctx, (double)N0, &mstats, &rs), "em_model_round");
+                mdl.rebuild(mstats);  // model.init(); collect(); finish()
+                model_dirty = true;
+                if (rank == 0) print_round(ROUND, rs);
+                tot = rs.totnum;
+                keep_going = ROUND < MIN_ROUND || (tot > 0 && ROUND < MAX_ROUND);
+            } else {
+                if (model_dirty) {
+                    push_model();
+                    check_rc(rsem_b200_calc_conprb(ctx), "calc_conprb");
+                    model_dirty = false;
+                }
+                int32_t ran = 0, stopped = 0;
+                check_rc(rsem_b200_em_rounds(ctx, ROUND, CHUNK, MIN_ROUND, MAX_ROUND, (double)N0, chunk_stats.data(), &ran, &stopped), "em_rounds");
+                if (rank == 0) for (int r = 0; r < ran; ++r) print_round(ROUND + r, chunk_stats[r]);
+                if (ran > 0) { ROUND += ran - 1; tot = chunk_stats[ran - 1].totnum; }
+                keep_going = !stopped;
+            }
+        }
+        // ---- .ofg inputs (EM.cpp:421-457): calcConProbs when the loop ended inside the model rounds
+        if (model_dirty) {
+            push_model();
+            check_rc(rsem_b200_calc_conprb(ctx), "calc_conprb");
+            model_dirty = false;
+        }
+        if (a.gibbsOut) check_rc(rsem_b200_download_conprb(ctx, conprb.data() + h0, ncpv.data() + r0), "download_conprb");
+        // ---- expected weights with the learned parameters (EM.cpp:460-478); counts are summed over ranks by the library
+        std::vector<double> th(M + 1), cnt(M + 1);
+        check_rc(rsem_b200_get_theta(ctx, th.data()), "get_theta");
+        check_rc(rsem_b200_expected_weights(ctx, cnt.data()), "expected_weights");
+        if (rank == 0) {
+            theta = th;
+            counts = cnt;
+            final_model = mdl;
+            totNum = tot;
+        }
+        rsem_b200_ctx_destroy(ctx);
+    };
+    if (world == 1) worker(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int r = 0; r < world; ++r) pool.emplace_back(worker, r);
+        for (auto& t : pool) t.join();
     }
+    model = final_model;
     if (totNum > 0) fprintf(stderr, "Warning: RSEM reaches %d iterations before meeting the convergence criteria.\n", MAX_ROUND);
-
-    // ---- .ofg (EM.cpp:421-457) ----
-    if (model_dirty) {  // calcConProbs when the loop ended inside the model rounds
-        push_model();
-        check_rc(rsem_b200_calc_conprb(ctx), "calc_conprb");
-        model_dirty = false;
-    }
-    std::vector<double> conprb(hits.H), ncpv(hits.N);
-    if (a.gibbsOut) {
-        check_rc(rsem_b200_download_conprb(ctx, conprb.data(), ncpv.data()), "download_conprb");
-        write_ofg(a.imdName + ".ofg", M, N0, hits, conprb, ncpv);
-    }
-
-    // ---- expected weights with the learned parameters (EM.cpp:460-478) ----
-    check_rc(rsem_b200_get_theta(ctx, theta.data()), "get_theta");
-    std::vector<double> counts(M + 1, 0.0);
-    check_rc(rsem_b200_expected_weights(ctx, counts.data()), "expected_weights");
+    if (a.gibbsOut) write_ofg(a.imdName + ".ofg", M, N0, hits, conprb, ncpv);
     counts[0] += N0;
 
     // ---- .theta (EM.cpp:484-500) ----
@@ -269,7 +343,6 @@ int main(int argc, char* argv[]) {
     model.write(a.statName + ".model");
     write_results_em(a.refName, a.imdName, transcripts, theta, eel, counts.data(), a.appendNames);
 
-    rsem_b200_ctx_destroy(ctx);
     const time_t t_end = time(NULL);
     printf("Time Used for EM.cpp : %d h %02d m %02d s\n", int((t_end - t_start) / 3600), int((t_end - t_start) % 3600 / 60), int((t_end - t_start) % 60));
     return 0;

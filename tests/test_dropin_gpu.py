@@ -130,3 +130,30 @@ def test_bam_flag_is_refused_loudly(workdir):
     base = rf.gen_dataset(str(workdir / "bam_base"), read_type=0, M=30, N1=100, N0=5)
     p = rf.run_em(base, 0, "ours", rounds=2, extra=["-b", "x.bam", "0"], check=False)
     assert p.returncode != 0 and "-b" in p.stderr
+
+
+def test_em_two_gpus_matches_reference(workdir):
+    """RSEM_B200_DEVICES=0,1: reads sharded over two GPUs (same rule as the reference's threads), counts and model
+    statistics summed with ncclAllReduce inside the library.  Needs a box with >= 2 GPUs (gpurun --gpus 2)."""
+    import rsem_b200
+    if rsem_b200.load_library().device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rt, opts = CASES["pe_q_rspd"]
+    base = rf.gen_dataset(str(workdir / "mgpu_base"), read_type=rt, seed=9, **opts)
+    ref, ours = rf.clone(base, str(workdir / "mgpu_ref")), rf.clone(base, str(workdir / "mgpu_ours"))
+    rf.run_em(ref, rt, "ref", rounds=14, threads=2)
+    os.environ["RSEM_B200_DEVICES"] = "0,1"
+    try:
+        po = rf.run_em(ours, rt, "ours", rounds=14)
+    finally:
+        del os.environ["RSEM_B200_DEVICES"]
+    assert "GPU 1 : N = " in po.stdout
+    raw_r, pol_r = rf.read_theta(f"{ref}/s.stat/s.theta")
+    raw_o, pol_o = rf.read_theta(f"{ours}/s.stat/s.theta")
+    assert rf.close_rel(raw_o, raw_r, 1e-6) and rf.close_rel(pol_o, pol_r, 1e-6)
+    mr, mo = rf.read_tokens(f"{ref}/s.stat/s.model"), rf.read_tokens(f"{ours}/s.stat/s.model")
+    assert np.all(np.abs(mo - mr) <= 1e-9 + 1e-6 * np.abs(mr))
+    _, _, rp_r, sid_r, c_r = rf.read_ofg(f"{ref}/s.temp/s.ofg")
+    _, _, rp_o, sid_o, c_o = rf.read_ofg(f"{ours}/s.temp/s.ofg")
+    assert np.array_equal(rp_r, rp_o) and np.array_equal(sid_r, sid_o) and np.all(np.abs(c_o - c_r) <= 1e-6 * np.abs(c_r))
+    _num_rows_close(rf.read_res(f"{ours}/s.temp/s.iso_res"), rf.read_res(f"{ref}/s.temp/s.iso_res"))
