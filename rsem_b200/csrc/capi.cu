@@ -74,6 +74,9 @@ void free_gibbs(rsem_b200_ctx* c) {
     if (c->gibbs.row_ptr) cudaFree(c->gibbs.row_ptr);
     if (c->gibbs.sid) cudaFree(c->gibbs.sid);
     if (c->gibbs.conprb) cudaFree(c->gibbs.conprb);
+    if (c->gibbs.order) cudaFree(c->gibbs.order);
+    if (c->gibbs.seg_start) cudaFree(c->gibbs.seg_start);
+    if (c->gibbs.blk_seg) cudaFree(c->gibbs.blk_seg);
     c->gibbs = DevGibbs{};
 }
 
@@ -549,6 +552,7 @@ int rsem_b200_gibbs_upload(rsem_b200_ctx* c, uint64_t N1, uint64_t E, int32_t M,
     c->gibbs.N1 = N1;
     c->gibbs.E = E;
     c->gibbs.M = M;
+    if (int rc = gibbs_prepare(c, row_ptr, sid)) return rc;
     return 0;
 }
 

@@ -94,6 +94,12 @@ struct DevGibbs {
     uint64_t* row_ptr = nullptr;
     int32_t* sid = nullptr;
     double* conprb = nullptr;
+    // component-parallel sampler (gibbs_kernels.cu): reads of a block grouped by connected component
+    int32_t* order = nullptr;      // N1 read ids: block by block, inside a block by (component, read id)
+    int32_t* seg_start = nullptr;  // n_segs + 1 offsets into `order`
+    int32_t* blk_seg = nullptr;    // n_blocks + 1 segment ranges
+    int32_t block_reads = 0, n_blocks = 0, n_segs = 0;
+    uint32_t max_len = 0;
 };
 
 }  // namespace rsem_b200
@@ -204,5 +210,6 @@ int model_launch_update(rsem_b200_ctx* ctx);
 
 // gibbs_kernels.cu
 int gibbs_run(rsem_b200_ctx* ctx, const rsem_b200_gibbs_params* p, rsem_b200_gibbs_out* out);
+int gibbs_prepare(rsem_b200_ctx* ctx, const uint64_t* row_ptr, const int32_t* sid);
 
 }  // namespace rsem_b200

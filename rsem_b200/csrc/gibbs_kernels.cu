@@ -17,6 +17,8 @@
 // The within-chain dependence (every draw reads counts written by the previous reads) makes this
 // latency-bound; the component-parallel exact scheme of SURVEY.md A.4 is the planned next step.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -227,6 +229,278 @@ __global__ void __launch_bounds__(kGibbsThreads) gibbs_chain_kernel(const GibbsA
     }
 }
 
+// ================================================================================================
+// Component-parallel EXACT sampler.
+//
+// Within a chain every draw reads the counts the previous reads wrote, so a sweep is sequential - but only
+// between reads that share a candidate transcript.  Reads of different connected components of the
+// read x transcript graph (noise transcript 0 excluded) touch disjoint counts and commute exactly.  The only
+// global coupling is the noise count c0 = counts[0], which enters every row that has a noise entry.
+//
+//   * Static, once per upload (gibbs_prepare, host): connected components (union-find over transcripts), the
+//     read sequence cut into blocks of `block_reads` consecutive reads, the reads of a block grouped by
+//     component in read order ("segments").
+//   * Per block, per chain: every segment is walked by ONE thread in read order with the live counts of its
+//     component and a SNAPSHOT of c0 taken at the start of the pass.  That is exactly the sequential result as
+//     long as no read of the block changes its noise membership.  Reads that do are recorded (atomicMin of their
+//     position p); after the pass everything after p is rolled back (z from the saved copy, counts re-adjusted -
+//     both component-private) and re-run with the corrected c0.  Each iteration is exact up to and including the
+//     next membership change, so the loop ends with the sequential state, bit for bit.
+//   * The i-th uniform of a sweep is the (sweep * N1 + i)-th output of the chain's MT19937; CTA 0 of the chain
+//     produces the block's uniforms (624-word regeneration by the whole CTA) before the pass.
+//   * A chain is served by `ctas_per_chain` co-resident CTAs (cooperative launch) that meet at a per-chain
+//     barrier in global memory; chains never synchronise with each other.
+// ================================================================================================
+constexpr int kPThreads = 256;
+
+struct ChainSync {
+    unsigned count, gen;       // barrier among the chain's CTAs
+    unsigned flip[2];          // smallest read position whose noise membership changed in the current pass
+    int err;
+    unsigned pad[3];
+};
+
+struct PArgs {
+    unsigned long long N1;
+    const unsigned long long* row_ptr;
+    const int* sid;
+    const double* conprb;
+    const int* order;
+    const int* seg_start;
+    const int* blk_seg;
+    int block_reads, n_blocks;
+    int M, burnin, gap, n_genes, n_chains, ctas_per_chain, chain_base;
+    const int* chain_samples;
+    const unsigned* chain_seeds;
+    const long long* chain_cv_offset;
+    double n0, totc;
+    const int* init_counts;
+    const double* alpha;
+    const double* eel;
+    const double* mw;
+    const int* gene_start;
+    int* counts;           // n_chains * (M + 1)
+    int* z;                // n_chains * N1
+    int* zsave;            // n_chains * block_reads
+    unsigned* ublk;        // n_chains * block_reads raw MT outputs
+    ChainSync* sync;       // n_chains
+    int* count_vectors;
+    double* acc;
+    double* theta_tmp;
+};
+
+__device__ __forceinline__ int ld_cg(const int* p) { return __ldcg(p); }
+__device__ __forceinline__ void st_cg(int* p, int v) { __stcg(p, v); }
+
+__device__ void chain_barrier(ChainSync* s, unsigned n_ctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned gen = *((volatile unsigned*)&s->gen);
+        if (atomicAdd(&s->count, 1u) == n_ctas - 1) {
+            s->count = 0;
+            __threadfence();
+            atomicAdd(&s->gen, 1u);
+        } else {
+            while (*((volatile unsigned*)&s->gen) == gen) {}
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// regenerate the 624 MT words with the whole CTA (three dependent phases + the last word)
+__device__ void mt_regenerate_cta(MtState& s) {
+    const int lo[4] = {0, 227, 454, 623}, hi[4] = {227, 454, 623, 624};
+    for (int p = 0; p < 4; ++p) {
+        const int k = lo[p] + (int)threadIdx.x;
+        unsigned v = 0;
+        if (k < hi[p]) v = mt_twist(s.mt[k], s.mt[(k + 1) % 624], s.mt[(k + 397) % 624]);
+        __syncthreads();
+        if (k < hi[p]) s.mt[k] = v;
+        __syncthreads();
+    }
+}
+
+// one draw by one thread, two passes over the row (no cumulative array is stored: the second pass recomputes the
+// same running sum, bit for bit).  c0_eff replaces counts[0].  Returns the chosen entry index.
+__device__ __forceinline__ int draw_one(const PArgs& a, const int* counts, unsigned long long fr, unsigned len,
+                                        bool use_counts, int c0_eff, unsigned raw, int* err) {
+    double total = 0.0;
+    for (unsigned k = 0; k < len; ++k) {
+        const int t = a.sid[fr + k];
+        const double c = a.conprb[fr + k];
+        const double v = use_counts ? __dmul_rn(__dadd_rn((double)(t == 0 ? c0_eff : ld_cg(counts + t)), a.alpha[t]), c) : c;
+        total = k ? __dadd_rn(v, total) : v;
+    }
+    const double prb = __dmul_rn(raw * (1.0 / 4294967296.0), total);
+    double run = 0.0;
+    for (unsigned k = 0; k < len; ++k) {
+        const int t = a.sid[fr + k];
+        const double c = a.conprb[fr + k];
+        const double v = use_counts ? __dmul_rn(__dadd_rn((double)(t == 0 ? c0_eff : ld_cg(counts + t)), a.alpha[t]), c) : c;
+        run = k ? __dadd_rn(v, run) : v;
+        if (run > prb) return (int)k;   // smallest index with arr[k] > prb (sampling.h:55-60)
+    }
+    *err = 3;                           // reference: assert(l < len)
+    return (int)len - 1;
+}
+
+__global__ void __launch_bounds__(kPThreads) gibbs_parallel_kernel(const PArgs a) {
+    __shared__ MtState mt;
+    __shared__ double sh_red[kPThreads / 32];
+    __shared__ int mt_idx_s;
+    const int chain = a.chain_base + blockIdx.x / a.ctas_per_chain;
+    const int cta = blockIdx.x % a.ctas_per_chain;
+    const unsigned n_ctas = a.ctas_per_chain;
+    const int tid = threadIdx.x;
+    const int M1 = a.M + 1;
+    const unsigned chain_threads = n_ctas * kPThreads, ctid = cta * kPThreads + tid;
+    int* counts = a.counts + (size_t)chain * M1;
+    int* z = a.z + (size_t)chain * a.N1;
+    int* zsave = a.zsave + (size_t)chain * a.block_reads;
+    unsigned* ublk = a.ublk + (size_t)chain * a.block_reads;
+    ChainSync* sy = a.sync + chain;
+    double* acc = a.acc + (size_t)chain * (4 * (size_t)M1 + a.n_genes);
+    double* theta = a.theta_tmp + (size_t)chain * 2 * M1;
+    double* fpkm = theta + M1;
+    const int n_samples = a.chain_samples[chain];
+    int* cv = a.count_vectors + a.chain_cv_offset[chain] * M1;
+
+    for (int i = ctid; i < M1; i += chain_threads) st_cg(counts + i, a.init_counts[i] + (i == 0 ? (int)a.n0 : 0));
+    if (cta == 0 && tid == 0) {
+        mt.mt[0] = a.chain_seeds[chain];
+        for (int k = 1; k < 624; ++k) mt.mt[k] = 1812433253u * (mt.mt[k - 1] ^ (mt.mt[k - 1] >> 30)) + (unsigned)k;
+        mt_idx_s = 624;
+    }
+    chain_barrier(sy, n_ctas);
+
+    const int chainlen = 1 + (n_samples - 1) * a.gap;
+    int kept = 0;
+    unsigned flip_parity = 0;
+    for (int round = 0; round <= a.burnin + chainlen; ++round) {   // round 0 = initial state from conprb alone
+        const bool use_counts = round > 0;
+        for (int b = 0; b < a.n_blocks; ++b) {
+            const unsigned long long i0 = (unsigned long long)b * a.block_reads;
+            const unsigned nb = (unsigned)min((unsigned long long)a.block_reads, a.N1 - i0);
+            // ---- uniforms of this block (CTA 0) and a copy of z for roll-backs (everyone)
+            if (cta == 0) {
+                unsigned done = 0;
+                while (done < nb) {
+                    if (mt_idx_s >= 624) {   // uniform across the CTA: mt_idx_s only changes between barriers
+                        mt_regenerate_cta(mt);
+                        if (tid == 0) mt_idx_s = 0;
+                        __syncthreads();
+                    }
+                    const int idx = mt_idx_s;
+                    const unsigned take = min((unsigned)(624 - idx), nb - done);
+                    for (unsigned k = tid; k < take; k += kPThreads) __stcg(ublk + done + k, mt_temper(mt.mt[idx + k]));
+                    __syncthreads();
+                    if (tid == 0) mt_idx_s = idx + (int)take;
+                    __syncthreads();
+                    done += take;
+                }
+            }
+            if (use_counts)
+                for (unsigned k = ctid; k < nb; k += chain_threads) st_cg(zsave + k, ld_cg(z + i0 + k));
+            if (cta == 0 && tid == 0) { sy->flip[0] = 0xffffffffu; sy->flip[1] = 0xffffffffu; }
+            chain_barrier(sy, n_ctas);
+
+            unsigned long long lo = i0;   // first position that still has to be (re)drawn
+            const int s0 = a.blk_seg[b], s1 = a.blk_seg[b + 1];
+            for (;;) {
+                const int c0 = ld_cg(counts);   // snapshot of the noise count, valid for every position >= lo
+                unsigned* flip = &sy->flip[flip_parity];
+                for (int sgm = s0 + (int)ctid; sgm < s1; sgm += (int)chain_threads) {
+                    for (int q = a.seg_start[sgm]; q < a.seg_start[sgm + 1]; ++q) {
+                        const unsigned long long i = (unsigned long long)a.order[q];
+                        if (i < lo) continue;
+                        const unsigned long long fr = a.row_ptr[i];
+                        const unsigned len = (unsigned)(a.row_ptr[i + 1] - fr);
+                        int zo = 0;
+                        if (use_counts) {
+                            zo = ld_cg(z + i);
+                            if (zo == 0) atomicSub(counts, 1); else st_cg(counts + zo, ld_cg(counts + zo) - 1);
+                        }
+                        const int l = draw_one(a, counts, fr, len, use_counts, c0 - (use_counts && zo == 0 ? 1 : 0),
+                                               __ldcg(ublk + (i - i0)), &sy->err);
+                        const int zn = a.sid[fr + l];
+                        st_cg(z + i, zn);
+                        if (zn == 0) atomicAdd(counts, 1); else st_cg(counts + zn, ld_cg(counts + zn) + 1);
+                        if (use_counts && ((zo == 0) != (zn == 0))) atomicMin(flip, (unsigned)(i - i0));
+                    }
+                }
+                chain_barrier(sy, n_ctas);
+                const unsigned p = *((volatile unsigned*)flip);
+                if (p == 0xffffffffu) break;
+                // ---- roll back everything after position p of the block, then redo it with the corrected c0
+                const unsigned long long redo = i0 + p + 1;
+                for (int sgm = s0 + (int)ctid; sgm < s1; sgm += (int)chain_threads) {
+                    for (int q = a.seg_start[sgm]; q < a.seg_start[sgm + 1]; ++q) {
+                        const unsigned long long i = (unsigned long long)a.order[q];
+                        if (i < redo || i < lo) continue;
+                        const int zn = ld_cg(z + i), zo = ld_cg(zsave + (i - i0));
+                        if (zn == 0) atomicSub(counts, 1); else st_cg(counts + zn, ld_cg(counts + zn) - 1);
+                        if (zo == 0) atomicAdd(counts, 1); else st_cg(counts + zo, ld_cg(counts + zo) + 1);
+                        st_cg(z + i, zo);
+                    }
+                }
+                if (cta == 0 && tid == 0) sy->flip[flip_parity ^ 1u] = 0xffffffffu;
+                flip_parity ^= 1u;
+                lo = redo;
+                chain_barrier(sy, n_ctas);
+                if (lo >= i0 + nb) break;
+            }
+            // leave both flip slots clean for the next block (done at its start)
+        }
+        if (round > a.burnin && (round - a.burnin - 1) % a.gap == 0) {   // Gibbs.cpp:313-346, by CTA 0 of the chain
+            if (cta == 0) {
+                double part = 0.0;
+                for (int i = tid; i < M1; i += kPThreads) {
+                    const int c = ld_cg(counts + i);
+                    cv[(size_t)kept * M1 + i] = c;
+                    double th = c < 0 ? 0.0 : ((double)c + a.alpha[i]) / a.totc;
+                    if (i > 0 && (a.mw[i] < kEpsilon || a.eel[i] < kEpsilon)) th = 0.0;
+                    else th = th / a.mw[i];
+                    theta[i] = th;
+                    part += th;
+                }
+                const double tsum = block_sum(part, sh_red);
+                part = 0.0;
+                for (int i = tid; i < M1; i += kPThreads) {
+                    const double th = theta[i] / tsum;
+                    theta[i] = th;
+                    if (i > 0 && a.eel[i] >= kEpsilon) part += th;
+                }
+                double denom = block_sum(part, sh_red);
+                if (denom < kEpsilon) denom = 1.0;
+                part = 0.0;
+                for (int i = tid; i < M1; i += kPThreads) {
+                    const double f = (i > 0 && a.eel[i] >= kEpsilon) ? (theta[i] / denom) * 1e9 / a.eel[i] : 0.0;
+                    fpkm[i] = f;
+                    part += f;
+                }
+                double fsum = block_sum(part, sh_red);
+                if (fsum < kEpsilon) fsum = 1.0;
+                for (int i = tid; i < M1; i += kPThreads) {
+                    const double c = (double)ld_cg(counts + i);
+                    acc[i] += c;
+                    acc[M1 + i] += c * c;
+                    acc[2 * (size_t)M1 + i] += i > 0 ? fpkm[i] / fsum * 1e6 : 0.0;
+                    acc[3 * (size_t)M1 + i] += fpkm[i];
+                }
+                for (int gi = tid; gi < a.n_genes; gi += kPThreads) {
+                    double c = 0.0;
+                    for (int j = a.gene_start[gi]; j < a.gene_start[gi + 1]; ++j) c += ld_cg(counts + j);
+                    acc[4 * (size_t)M1 + gi] += c * c;
+                }
+            }
+            ++kept;
+            chain_barrier(sy, n_ctas);
+        }
+    }
+}
+
 template <class T>
 int to_dev(T** d, const T* h, size_t n, cudaStream_t s) {
     RB_CUDA(cudaMalloc(d, std::max<size_t>(n, 1) * sizeof(T)));
@@ -236,7 +510,7 @@ int to_dev(T** d, const T* h, size_t n, cudaStream_t s) {
 
 }  // namespace
 
-int gibbs_run(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p, rsem_b200_gibbs_out* out) {
+static int gibbs_run_serial(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p, rsem_b200_gibbs_out* out) {
     const DevGibbs& g = c->gibbs;
     const int M1 = p->M + 1, nc = p->n_chains;
     long long total_samples = 0;
@@ -327,6 +601,180 @@ int gibbs_run(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p, rsem_b200_gibbs
         for (int gi = 0; gi < p->n_genes; ++gi) out->sum_gene_c2[gi] += b[4 * (size_t)M1 + gi];
     }
     return 0;
+}
+
+
+// ---- static preparation for the component-parallel sampler (host) ---------------------------------------------
+int gibbs_prepare(rsem_b200_ctx* c, const uint64_t* row_ptr, const int32_t* sid) {
+    DevGibbs& g = c->gibbs;
+    const uint64_t N1 = g.N1;
+    const int M = g.M;
+    if (N1 == 0) return 0;
+    if (N1 > 0x7fffffffull) { set_error("gibbs: more than 2^31 reads are not supported"); return RSEM_B200_ERR_UNSUPPORTED; }
+    // connected components of the read x transcript graph, noise transcript excluded (union-find with path halving)
+    std::vector<int32_t> parent((size_t)M + 1);
+    for (int t = 0; t <= M; ++t) parent[t] = t;
+    auto find = [&](int32_t x) {
+        while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+        return x;
+    };
+    uint64_t max_len = 1;
+    for (uint64_t i = 0; i < N1; ++i) {
+        int32_t first = 0;
+        max_len = std::max(max_len, row_ptr[i + 1] - row_ptr[i]);
+        for (uint64_t j = row_ptr[i]; j < row_ptr[i + 1]; ++j) {
+            const int32_t t = sid[j];
+            if (t < 0 || t > M) { set_error("gibbs: transcript id out of range in the .ofg matrix"); return RSEM_B200_ERR_ARG; }
+            if (t == 0) continue;
+            if (first == 0) first = find(t);
+            else {
+                const int32_t r = find(t);
+                if (r != first) parent[r] = first;
+            }
+        }
+    }
+    g.max_len = (uint32_t)max_len;
+    // component key of a read: root of its first non-noise transcript; reads with only the noise entry get a unique key
+    std::vector<int64_t> key(N1);
+    for (uint64_t i = 0; i < N1; ++i) {
+        int64_t k = -(int64_t)i - 1;
+        for (uint64_t j = row_ptr[i]; j < row_ptr[i + 1]; ++j)
+            if (sid[j] != 0) { k = find(sid[j]); break; }
+        key[i] = k;
+    }
+    int B = 16384;
+    if (const char* e = getenv("RSEM_B200_GIBBS_BLOCK")) { const int v = atoi(e); if (v >= 32) B = v; }
+    const int n_blocks = (int)((N1 + B - 1) / B);
+    std::vector<int32_t> order(N1), seg_start, blk_seg(n_blocks + 1);
+    seg_start.reserve(N1 / 4 + 16);
+    std::vector<int32_t> idx;
+    for (int b = 0; b < n_blocks; ++b) {
+        const uint64_t i0 = (uint64_t)b * B, i1 = std::min<uint64_t>(N1, i0 + B);
+        idx.resize(i1 - i0);
+        for (uint64_t i = i0; i < i1; ++i) idx[i - i0] = (int32_t)i;
+        std::stable_sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return key[x] < key[y]; });
+        blk_seg[b] = (int32_t)seg_start.size();
+        for (uint64_t q = 0; q < idx.size(); ++q) {
+            if (q == 0 || key[idx[q]] != key[idx[q - 1]]) seg_start.push_back((int32_t)(i0 + q));
+            order[i0 + q] = idx[q];
+        }
+    }
+    blk_seg[n_blocks] = (int32_t)seg_start.size();
+    seg_start.push_back((int32_t)N1);
+    g.block_reads = B;
+    g.n_blocks = n_blocks;
+    g.n_segs = (int32_t)seg_start.size() - 1;
+    RB_CUDA(cudaMalloc(&g.order, N1 * sizeof(int32_t)));
+    RB_CUDA(cudaMalloc(&g.seg_start, seg_start.size() * sizeof(int32_t)));
+    RB_CUDA(cudaMalloc(&g.blk_seg, blk_seg.size() * sizeof(int32_t)));
+    RB_CUDA(cudaMemcpyAsync(g.order, order.data(), N1 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    RB_CUDA(cudaMemcpyAsync(g.seg_start, seg_start.data(), seg_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    RB_CUDA(cudaMemcpyAsync(g.blk_seg, blk_seg.data(), blk_seg.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p, rsem_b200_gibbs_out* out) {
+    const DevGibbs& g = c->gibbs;
+    const int M1 = p->M + 1, nc = p->n_chains;
+    long long total_samples = 0;
+    std::vector<long long> cv_off(nc);
+    for (int t = 0; t < nc; ++t) { cv_off[t] = total_samples; total_samples += p->chain_samples[t]; }
+    const size_t acc_per = 4 * (size_t)M1 + p->n_genes;
+
+    PArgs a{};
+    a.N1 = g.N1;
+    a.row_ptr = reinterpret_cast<const unsigned long long*>(g.row_ptr);
+    a.sid = g.sid; a.conprb = g.conprb; a.order = g.order; a.seg_start = g.seg_start; a.blk_seg = g.blk_seg;
+    a.block_reads = g.block_reads; a.n_blocks = g.n_blocks;
+    a.M = p->M; a.burnin = p->burnin; a.gap = p->gap; a.n_genes = p->n_genes; a.n_chains = nc;
+    a.n0 = p->n0; a.totc = p->totc;
+
+    int *d_samples = nullptr, *d_init = nullptr, *d_gene = nullptr, *d_counts = nullptr, *d_z = nullptr, *d_cv = nullptr, *d_zsave = nullptr;
+    unsigned *d_seeds = nullptr, *d_u = nullptr;
+    long long* d_off = nullptr;
+    ChainSync* d_sync = nullptr;
+    double *d_alpha = nullptr, *d_eel = nullptr, *d_mw = nullptr, *d_acc = nullptr, *d_tmp = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaFree(d_samples); cudaFree(d_init); cudaFree(d_gene); cudaFree(d_counts); cudaFree(d_z); cudaFree(d_cv); cudaFree(d_zsave);
+        cudaFree(d_seeds); cudaFree(d_u); cudaFree(d_off); cudaFree(d_sync); cudaFree(d_alpha); cudaFree(d_eel); cudaFree(d_mw);
+        cudaFree(d_acc); cudaFree(d_tmp);
+    };
+#define RB_TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
+#define RB_TRYC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #x, __FILE__, __LINE__); } } while (0)
+    RB_TRY(to_dev(&d_samples, p->chain_samples, nc, c->stream));
+    RB_TRY(to_dev(&d_seeds, p->chain_seeds, nc, c->stream));
+    RB_TRY(to_dev(&d_off, cv_off.data(), nc, c->stream));
+    RB_TRY(to_dev(&d_init, p->init_counts, M1, c->stream));
+    RB_TRY(to_dev(&d_alpha, p->pseudo_counts, M1, c->stream));
+    RB_TRY(to_dev(&d_eel, p->eel, M1, c->stream));
+    RB_TRY(to_dev(&d_mw, p->mw, M1, c->stream));
+    RB_TRY(to_dev(&d_gene, p->gene_start, (size_t)p->n_genes + 1, c->stream));
+    RB_TRYC(cudaMalloc(&d_counts, (size_t)nc * M1 * sizeof(int)));
+    RB_TRYC(cudaMalloc(&d_z, std::max<size_t>((size_t)nc * g.N1, 1) * sizeof(int)));
+    RB_TRYC(cudaMalloc(&d_zsave, (size_t)nc * g.block_reads * sizeof(int)));
+    RB_TRYC(cudaMalloc(&d_u, (size_t)nc * g.block_reads * sizeof(unsigned)));
+    RB_TRYC(cudaMalloc(&d_sync, (size_t)nc * sizeof(ChainSync)));
+    RB_TRYC(cudaMalloc(&d_cv, std::max<size_t>((size_t)total_samples * M1, 1) * sizeof(int)));
+    RB_TRYC(cudaMalloc(&d_acc, (size_t)nc * acc_per * sizeof(double)));
+    RB_TRYC(cudaMalloc(&d_tmp, (size_t)nc * 2 * M1 * sizeof(double)));
+    RB_TRYC(cudaMemsetAsync(d_acc, 0, (size_t)nc * acc_per * sizeof(double), c->stream));
+    RB_TRYC(cudaMemsetAsync(d_sync, 0, (size_t)nc * sizeof(ChainSync), c->stream));
+    a.chain_samples = d_samples; a.chain_seeds = d_seeds; a.chain_cv_offset = d_off; a.init_counts = d_init;
+    a.alpha = d_alpha; a.eel = d_eel; a.mw = d_mw; a.gene_start = d_gene; a.counts = d_counts; a.z = d_z;
+    a.zsave = d_zsave; a.ublk = d_u; a.sync = d_sync; a.count_vectors = d_cv; a.acc = d_acc; a.theta_tmp = d_tmp;
+
+    // co-resident CTAs: chains are run in waves of at most sm_count, every chain gets the same number of CTAs
+    int per_sm = 0;
+    RB_TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_parallel_kernel, kPThreads, 0));
+    const int resident = std::max(1, per_sm) * c->sm_count;
+    const double segs_per_block = (double)g.n_segs / std::max(1, g.n_blocks);
+    for (int base = 0; base < nc;) {
+        const int wave = std::min(nc - base, resident);
+        int ctas = std::max(1, std::min(resident / wave, (int)(segs_per_block / kPThreads) + 1));
+        if (const char* e = getenv("RSEM_B200_GIBBS_CTAS")) { const int v = atoi(e); if (v >= 1 && v * wave <= resident) ctas = v; }
+        a.chain_base = base;
+        a.ctas_per_chain = ctas;
+        void* kargs[] = {(void*)&a};
+        RB_TRYC(cudaLaunchCooperativeKernel((void*)gibbs_parallel_kernel, dim3(wave * ctas), dim3(kPThreads), kargs, 0, c->stream));
+        c->launches++;
+        base += wave;
+    }
+    std::vector<double> h_acc((size_t)nc * acc_per);
+    std::vector<ChainSync> h_sync(nc);
+    RB_TRYC(cudaMemcpyAsync(h_acc.data(), d_acc, h_acc.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RB_TRYC(cudaMemcpyAsync(out->count_vectors, d_cv, (size_t)total_samples * M1 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    RB_TRYC(cudaMemcpyAsync(h_sync.data(), d_sync, (size_t)nc * sizeof(ChainSync), cudaMemcpyDeviceToHost, c->stream));
+    RB_TRYC(cudaStreamSynchronize(c->stream));
+    cleanup();
+#undef RB_TRY
+#undef RB_TRYC
+    for (int t = 0; t < nc; ++t)
+        if (h_sync[t].err) {
+            set_error("gibbs: categorical draw fell off the cumulative array (reference: assert(l < len), sampling.h:62)");
+            return RSEM_B200_ERR_ARG;
+        }
+    for (int i = 0; i < M1; ++i) out->sum_c[i] = out->sum_c2[i] = out->sum_tpm[i] = out->sum_fpkm[i] = 0.0;
+    for (int gi = 0; gi < p->n_genes; ++gi) out->sum_gene_c2[gi] = 0.0;
+    for (int t = 0; t < nc; ++t) {   // per-chain accumulators in chain order (Gibbs.cpp:372-397)
+        const double* b = h_acc.data() + (size_t)t * acc_per;
+        for (int i = 0; i < M1; ++i) {
+            out->sum_c[i] += b[i];
+            out->sum_c2[i] += b[M1 + i];
+            out->sum_tpm[i] += b[2 * (size_t)M1 + i];
+            out->sum_fpkm[i] += b[3 * (size_t)M1 + i];
+        }
+        for (int gi = 0; gi < p->n_genes; ++gi) out->sum_gene_c2[gi] += b[4 * (size_t)M1 + gi];
+    }
+    return 0;
+}
+
+int gibbs_run(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p, rsem_b200_gibbs_out* out) {
+    const char* mode = getenv("RSEM_B200_GIBBS");   // "serial" = the one-warp-per-chain kernel (cross-check / debugging)
+    if (mode && !strcmp(mode, "serial")) return gibbs_run_serial(c, p, out);
+    if (c->gibbs.N1 == 0 || !c->gibbs.order) return gibbs_run_serial(c, p, out);
+    return gibbs_run_parallel(c, p, out);
 }
 
 }  // namespace rsem_b200

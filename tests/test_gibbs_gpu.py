@@ -1,0 +1,111 @@
+"""K5/K6 through the C ABI against the CPU oracle: same seeds -> the same draws (count vectors bit-identical),
+including matrices where reads move in and out of the noise transcript all the time (the case the
+component-parallel sampler has to roll back and redo)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from rsem_b200.capi import GibbsOut, GibbsParams
+
+pytestmark = pytest.mark.gpu
+
+
+def _ofg_like(N, M, deg, seed, noise_scale):
+    """rows of (sid, conprb) with the noise entry first (Gibbs.cpp:119-131); noise_scale moves the noise weight
+    from negligible to dominant so that membership changes are rare / frequent"""
+    rng = np.random.default_rng(seed)
+    row_ptr, sid, conprb, ncpv = synth.random_matrix(N, M, deg, seed=seed, tiny_frac=0.0)
+    conprb = np.where(conprb <= 0, 1e-30, conprb)
+    rows_sid, rows_val, rp = [], [], [0]
+    for i in range(N):
+        a, b = int(row_ptr[i]), int(row_ptr[i + 1])
+        s, v = list(np.abs(sid[a:b])), list(conprb[a:b])
+        if rng.random() < 0.9:
+            s.insert(0, 0)
+            v.insert(0, float(np.median(conprb[a:b]) * noise_scale * rng.uniform(0.1, 10)))
+        rows_sid += s
+        rows_val += v
+        rp.append(len(rows_sid))
+    return np.array(rp, np.uint64), np.array(rows_sid, np.int32), np.array(rows_val, np.float64)
+
+
+def _run_gpu(ctx, rp, sid, val, M, n0, init, alpha, totc, eel, mw, genes, burnin, gap, samples, seeds):
+    ctx.gibbs_upload(rp, sid, val, M)
+    nc = len(samples)
+    samples = np.ascontiguousarray(samples, np.int32)
+    seeds = np.ascontiguousarray(seeds, np.uint32)
+    init, genes = np.ascontiguousarray(init, np.int32), np.ascontiguousarray(genes, np.int32)
+    alpha, eel, mw = (np.ascontiguousarray(x, np.float64) for x in (alpha, eel, mw))
+    p = GibbsParams()
+    p.M, p.burnin, p.gap, p.n_chains = M, burnin, gap, nc
+    p.chain_samples = samples.ctypes.data_as(C.POINTER(C.c_int32))
+    p.chain_seeds = seeds.ctypes.data_as(C.POINTER(C.c_uint32))
+    p.n0, p.totc = n0, totc
+    p.init_counts = init.ctypes.data_as(C.POINTER(C.c_int32))
+    p.pseudo_counts = alpha.ctypes.data_as(C.POINTER(C.c_double))
+    p.eel, p.mw = eel.ctypes.data_as(C.POINTER(C.c_double)), mw.ctypes.data_as(C.POINTER(C.c_double))
+    p.n_genes = len(genes) - 1
+    p.gene_start = genes.ctypes.data_as(C.POINTER(C.c_int32))
+    total = int(samples.sum())
+    cv = np.zeros((total, M + 1), np.int32)
+    sums = [np.zeros(M + 1) for _ in range(4)] + [np.zeros(len(genes) - 1)]
+    o = GibbsOut()
+    o.count_vectors = cv.ctypes.data_as(C.POINTER(C.c_int32))
+    o.sum_c, o.sum_c2, o.sum_tpm, o.sum_fpkm, o.sum_gene_c2 = (s.ctypes.data_as(C.POINTER(C.c_double)) for s in sums)
+    ctx.gibbs_run(p, o)
+    return cv, sums
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    import rsem_b200
+    c = rsem_b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("mode", ["parallel", "serial"])
+@pytest.mark.parametrize("noise_scale,block", [(1e-30, 0), (1.0, 0), (1.0, 64), (30.0, 256)])
+def test_chains_match_oracle(ctx, oracle, mode, noise_scale, block, monkeypatch):
+    N, M = 3000, 150
+    rp, sid, val = _ofg_like(N, M, 4, seed=int(noise_scale * 7) + 3, noise_scale=noise_scale)
+    n0 = 40.0
+    init = np.zeros(M + 1, np.int32)
+    init[[5, 77]] = -1                                   # omitted transcripts never appear in a row
+    keep = ~np.isin(sid, [5, 77])
+    # drop omitted ids from the rows
+    new_rp = [0]
+    for i in range(N):
+        new_rp.append(new_rp[-1] + int(keep[int(rp[i]):int(rp[i + 1])].sum()))
+    rp, sid, val = np.array(new_rp, np.uint64), sid[keep], val[keep]
+    if np.any(np.diff(rp.astype(np.int64)) == 0):
+        pytest.skip("generator produced an empty row")
+    alpha = np.full(M + 1, 0.7)
+    totc = (M + 1 - 2) * 0.7 + n0 + N
+    rng = np.random.default_rng(1)
+    eel = np.concatenate([[0.0], rng.uniform(200, 2000, M)])
+    mw = np.ones(M + 1)
+    genes = np.arange(1, M + 2, 3, dtype=np.int32)
+    genes[-1] = M + 1
+    samples, burnin, gap = [3, 2, 2], 6, 2
+    seeds = oracle.chain_seeds(2024, 3)
+    monkeypatch.setenv("RSEM_B200_GIBBS", mode)
+    if block:
+        monkeypatch.setenv("RSEM_B200_GIBBS_BLOCK", str(block))
+    else:
+        monkeypatch.delenv("RSEM_B200_GIBBS_BLOCK", raising=False)
+    cv, sums = _run_gpu(ctx, rp, sid, val, M, n0, init, alpha, totc, eel, mw, genes, burnin, gap, samples, seeds)
+    at, ref_sums = 0, None
+    for t, ns in enumerate(samples):
+        cv_ref, s = oracle.gibbs_chain(rp, sid, val, M, n0, init, alpha, totc, eel, mw, genes, burnin, gap, ns, int(seeds[t]))
+        assert np.array_equal(cv[at:at + ns], cv_ref), f"chain {t} differs"
+        at += ns
+        ref_sums = s if ref_sums is None else [x + y for x, y in zip(ref_sums, s)]
+    for got, ref in zip(sums, ref_sums):
+        assert np.allclose(got, ref, rtol=1e-9, atol=1e-9)
+    # the noise count really moves in the stressed cases (otherwise the roll-back path is not exercised)
+    if noise_scale >= 1.0:
+        assert len(set(cv[:, 0].tolist())) > 1
