@@ -75,6 +75,9 @@ void free_gibbs(rsem_b200_ctx* c) {
     if (c->gibbs.sid) cudaFree(c->gibbs.sid);
     if (c->gibbs.conprb) cudaFree(c->gibbs.conprb);
     if (c->gibbs.order) cudaFree(c->gibbs.order);
+    if (c->gibbs.p_off) cudaFree(c->gibbs.p_off);
+    if (c->gibbs.p_sid) cudaFree(c->gibbs.p_sid);
+    if (c->gibbs.p_con) cudaFree(c->gibbs.p_con);
     if (c->gibbs.seg_start) cudaFree(c->gibbs.seg_start);
     if (c->gibbs.blk_seg) cudaFree(c->gibbs.blk_seg);
     c->gibbs = DevGibbs{};

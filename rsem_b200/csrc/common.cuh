@@ -96,6 +96,9 @@ struct DevGibbs {
     double* conprb = nullptr;
     // component-parallel sampler (gibbs_kernels.cu): reads of a block grouped by connected component
     int32_t* order = nullptr;      // N1 read ids: block by block, inside a block by (component, read id)
+    uint64_t* p_off = nullptr;     // rows re-laid in that slot order
+    int32_t* p_sid = nullptr;
+    double* p_con = nullptr;
     int32_t* seg_start = nullptr;  // n_segs + 1 offsets into `order`
     int32_t* blk_seg = nullptr;    // n_blocks + 1 segment ranges
     int32_t block_reads = 0, n_blocks = 0, n_segs = 0;

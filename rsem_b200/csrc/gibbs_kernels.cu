@@ -17,6 +17,7 @@
 // The within-chain dependence (every draw reads counts written by the previous reads) makes this
 // latency-bound; the component-parallel exact scheme of SURVEY.md A.4 is the planned next step.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -70,16 +71,26 @@ __device__ void mt_regenerate(MtState& s, int lane) {
     // phase 2: k in [227, 454) needs old[k], old[k+1], new[k-227]
     // phase 3: k in [454, 623) needs old[k], old[k+1], new[k-227]
     // phase 4: k = 623 needs old[623], new[0], new[396]
-    const int lo[4] = {0, 227, 454, 623}, hi[4] = {227, 454, 623, 624};
-    for (int p = 0; p < 4; ++p) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const int lo = 227 * p, hi = p == 2 ? 623 : 227 * (p + 1);
         unsigned v[8];
-        int n = 0;
-        for (int k = lo[p] + lane; k < hi[p]; k += 32) v[n++] = mt_twist(s.mt[k], s.mt[(k + 1) % 624], s.mt[(k + 397) % 624]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = lo + lane + 32 * j;
+            const int k3 = k + 397 >= 624 ? k + 397 - 624 : k + 397;
+            v[j] = k < hi ? mt_twist(s.mt[k], s.mt[k + 1], s.mt[k3]) : 0u;
+        }
         __syncwarp();
-        n = 0;
-        for (int k = lo[p] + lane; k < hi[p]; k += 32) s.mt[k] = v[n++];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = lo + lane + 32 * j;
+            if (k < hi) s.mt[k] = v[j];
+        }
         __syncwarp();
     }
+    if (lane == 0) s.mt[623] = mt_twist(s.mt[623], s.mt[0], s.mt[396]);
+    __syncwarp();
 }
 
 __device__ __forceinline__ unsigned mt_temper(unsigned y) {
@@ -258,6 +269,7 @@ struct ChainSync {
     unsigned flip[2];          // smallest read position whose noise membership changed in the current pass
     int err;
     unsigned pad[3];
+    unsigned long long prof[8];   // clock64 totals of CTA 0: rng, copy+barrier, pass, pass barrier, rollback, samples
 };
 
 struct PArgs {
@@ -265,7 +277,10 @@ struct PArgs {
     const unsigned long long* row_ptr;
     const int* sid;
     const double* conprb;
-    const int* order;
+    const int* order;                   // read id of slot q (block by block, inside a block by component)
+    const unsigned long long* p_off;    // N1 + 1 entry offsets of the slots, rows stored in slot order
+    const int* p_sid;
+    const double* p_con;
     const int* seg_start;
     const int* blk_seg;
     int block_reads, n_blocks;
@@ -280,9 +295,9 @@ struct PArgs {
     const double* mw;
     const int* gene_start;
     int* counts;           // n_chains * (M + 1)
-    int* z;                // n_chains * N1
+    int* z;                // n_chains * N1, indexed by SLOT (not by read id)
     int* zsave;            // n_chains * block_reads
-    unsigned* ublk;        // n_chains * block_reads raw MT outputs
+    unsigned* ublk;        // n_chains * 2 * block_reads raw MT outputs (double buffered)
     ChainSync* sync;       // n_chains
     int* count_vectors;
     double* acc;
@@ -322,28 +337,155 @@ __device__ void mt_regenerate_cta(MtState& s) {
     }
 }
 
-// one draw by one thread, two passes over the row (no cumulative array is stored: the second pass recomputes the
-// same running sum, bit for bit).  c0_eff replaces counts[0].  Returns the chosen entry index.
-__device__ __forceinline__ int draw_one(const PArgs& a, const int* counts, unsigned long long fr, unsigned len,
-                                        bool use_counts, int c0_eff, unsigned raw, int* err) {
+// A thread walks the reads of one (block, component) segment in order.  The static part of a read (ids, conprb,
+// its uniform, its previous assignment) does not depend on the counts, so the next read's row is loaded into
+// registers while the current one is drawn: the only memory round trip left on the dependent chain of a read is
+// the gather of its candidates' counts.  Rows of up to kRowRegs entries take this register path; longer rows take
+// the generic two-pass loop that recomputes the same running sum, bit for bit.
+constexpr int kRowRegs = 12;
+
+struct RowRegs {
+    int i;                 // read id (position in the sweep order)
+    unsigned len;
+    unsigned long long off;
+    int zo;                // current assignment
+    unsigned raw;          // MT19937 output for this read in this sweep
+    int t[kRowRegs];
+    double c[kRowRegs];
+};
+
+__device__ __forceinline__ void load_row(const PArgs& a, const int* z, const unsigned* ublk, unsigned long long i0, int q,
+                                         bool use_counts, RowRegs& r) {
+    r.i = a.order[q];
+    r.off = a.p_off[q];
+    r.len = (unsigned)(a.p_off[q + 1] - r.off);
+    r.zo = use_counts ? ld_cg(z + q) : 0;
+    r.raw = __ldcg(ublk + ((unsigned long long)r.i - i0));
+#pragma unroll
+    for (int k = 0; k < kRowRegs; ++k) {
+        r.t[k] = k < (int)r.len ? a.p_sid[r.off + k] : 0;
+        r.c[k] = k < (int)r.len ? a.p_con[r.off + k] : 0.0;
+    }
+}
+
+// returns the new assignment; updates the counts of the component (plain stores: component-private) and counts[0]
+// (atomics: shared by all components).  c0 = snapshot of the noise count.
+// The row is processed in chunks of kRowRegs entries: ids / conprb of a chunk with independent loads (the first chunk
+// was prefetched with the row), then the counts and alphas of the chunk with independent gathers, then the
+// left-to-right running sum.  The running sums and the counts seen are kept in a per-thread local array so that the
+// search needs no second trip to memory.  All lanes run the same code; rows differ only in the number of chunks.
+constexpr int kMaxLocal = 8 * kRowRegs;   // rows up to 96 entries; longer ones take the generic loop below
+
+__device__ __forceinline__ int draw_row(const PArgs& a, int* counts, const RowRegs& r, bool use_counts, int c0, int* err) {
+    const double u = r.raw * (1.0 / 4294967296.0);
+    const int zo = r.zo;
+    if (r.len <= kMaxLocal) {
+        double arr[kMaxLocal];
+        int seen[kMaxLocal];
+        double run = 0.0;
+        int cnt_zo = 0;
+        for (unsigned base = 0; base < r.len; base += kRowRegs) {
+            int t[kRowRegs];
+            double c[kRowRegs];
+            if (base == 0) {
+#pragma unroll
+                for (int k = 0; k < kRowRegs; ++k) { t[k] = r.t[k]; c[k] = r.c[k]; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kRowRegs; ++k) {
+                    const bool in = base + k < r.len;
+                    t[k] = in ? a.p_sid[r.off + base + k] : 0;
+                    c[k] = in ? a.p_con[r.off + base + k] : 0.0;
+                }
+            }
+            if (use_counts) {
+                int cnt[kRowRegs];
+                double al[kRowRegs];
+#pragma unroll
+                for (int k = 0; k < kRowRegs; ++k) {
+                    cnt[k] = (base + k < r.len && t[k] != 0) ? ld_cg(counts + t[k]) : c0;
+                    al[k] = a.alpha[t[k]];
+                }
+#pragma unroll
+                for (int k = 0; k < kRowRegs; ++k) {
+                    if (t[k] == zo) cnt[k] -= 1;   // --counts[z_i] (Gibbs.cpp:298), seen by every entry of that transcript
+                    if (base + k < r.len && t[k] == zo) cnt_zo = cnt[k];
+                    c[k] = __dmul_rn(__dadd_rn((double)cnt[k], al[k]), c[k]);
+                    seen[base + k] = cnt[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kRowRegs; ++k) {   // left-to-right running sum; slots beyond len repeat the last value
+                if (base + k < r.len) run = (base + k) ? __dadd_rn(c[k], run) : c[k];
+                arr[base + k] = run;
+            }
+        }
+        const double prb = __dmul_rn(u, run);
+        int l = -1;
+        for (unsigned k = 0; k < r.len; ++k)
+            if (arr[k] > prb) { l = (int)k; break; }   // smallest index with arr[k] > prb (sampling.h:55-60)
+        if (l < 0) { *err = 3; l = (int)r.len - 1; }   // reference: assert(l < len)
+        const int zn = l < kRowRegs ? 0 : a.p_sid[r.off + l];
+        int zn_fast = 0;
+#pragma unroll
+        for (int k = 0; k < kRowRegs; ++k) if (k == l) zn_fast = r.t[k];
+        const int znew = l < kRowRegs ? zn_fast : zn;
+        if (use_counts) {
+            if (znew != zo) {
+                if (zo == 0) atomicSub(counts, 1); else st_cg(counts + zo, cnt_zo);
+                if (znew == 0) atomicAdd(counts, 1); else st_cg(counts + znew, seen[l] + 1);
+            }
+        } else {
+            if (znew == 0) atomicAdd(counts, 1); else st_cg(counts + znew, ld_cg(counts + znew) + 1);
+        }
+        return znew;
+    }
+    // ---- very long rows: generic two-pass loop
+    if (use_counts) {
+        if (zo == 0) atomicSub(counts, 1); else st_cg(counts + zo, ld_cg(counts + zo) - 1);
+    }
+    const int c0_eff = c0 - (use_counts && zo == 0 ? 1 : 0);
     double total = 0.0;
-    for (unsigned k = 0; k < len; ++k) {
-        const int t = a.sid[fr + k];
-        const double c = a.conprb[fr + k];
+    for (unsigned k = 0; k < r.len; ++k) {
+        const int t = a.p_sid[r.off + k];
+        const double c = a.p_con[r.off + k];
         const double v = use_counts ? __dmul_rn(__dadd_rn((double)(t == 0 ? c0_eff : ld_cg(counts + t)), a.alpha[t]), c) : c;
         total = k ? __dadd_rn(v, total) : v;
     }
-    const double prb = __dmul_rn(raw * (1.0 / 4294967296.0), total);
+    const double prb = __dmul_rn(u, total);
     double run = 0.0;
-    for (unsigned k = 0; k < len; ++k) {
-        const int t = a.sid[fr + k];
-        const double c = a.conprb[fr + k];
+    int l = -1;
+    for (unsigned k = 0; k < r.len; ++k) {
+        const int t = a.p_sid[r.off + k];
+        const double c = a.p_con[r.off + k];
         const double v = use_counts ? __dmul_rn(__dadd_rn((double)(t == 0 ? c0_eff : ld_cg(counts + t)), a.alpha[t]), c) : c;
         run = k ? __dadd_rn(v, run) : v;
-        if (run > prb) return (int)k;   // smallest index with arr[k] > prb (sampling.h:55-60)
+        if (run > prb) { l = (int)k; break; }
     }
-    *err = 3;                           // reference: assert(l < len)
-    return (int)len - 1;
+    if (l < 0) { *err = 3; l = (int)r.len - 1; }
+    const int zn = a.p_sid[r.off + l];
+    if (zn == 0) atomicAdd(counts, 1); else st_cg(counts + zn, ld_cg(counts + zn) + 1);
+    return zn;
+}
+
+// `n` successive outputs of the chain's MT19937 (tempered, raw 32 bit) by one warp
+__device__ void fill_uniforms(MtState& mt, int& mt_idx_s, unsigned* dst, unsigned n, int lane) {
+    int idx = mt_idx_s;
+    unsigned done = 0;
+    while (done < n) {
+        if (idx >= 624) {
+            mt_regenerate(mt, lane);
+            idx = 0;
+        }
+        const unsigned take = min((unsigned)(624 - idx), n - done);
+        for (unsigned k = lane; k < take; k += 32) __stcg(dst + done + k, mt_temper(mt.mt[idx + k]));
+        __syncwarp();
+        idx += (int)take;
+        done += take;
+    }
+    __syncwarp();
+    if (lane == 0) mt_idx_s = idx;
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(kPThreads) gibbs_parallel_kernel(const PArgs a) {
@@ -356,10 +498,13 @@ __global__ void __launch_bounds__(kPThreads) gibbs_parallel_kernel(const PArgs a
     const int tid = threadIdx.x;
     const int M1 = a.M + 1;
     const unsigned chain_threads = n_ctas * kPThreads, ctid = cta * kPThreads + tid;
+    // segment walkers: every thread of the chain except the generator warp (warp 0 of CTA 0)
+    const bool is_gen = cta == 0 && tid < 32;
+    const unsigned n_workers = chain_threads - 32, wid = ctid - 32;
+    unsigned gblock = 0;   // running block number over all sweeps (parity selects the uniform buffer)
     int* counts = a.counts + (size_t)chain * M1;
     int* z = a.z + (size_t)chain * a.N1;
     int* zsave = a.zsave + (size_t)chain * a.block_reads;
-    unsigned* ublk = a.ublk + (size_t)chain * a.block_reads;
     ChainSync* sy = a.sync + chain;
     double* acc = a.acc + (size_t)chain * (4 * (size_t)M1 + a.n_genes);
     double* theta = a.theta_tmp + (size_t)chain * 2 * M1;
@@ -383,66 +528,68 @@ __global__ void __launch_bounds__(kPThreads) gibbs_parallel_kernel(const PArgs a
         for (int b = 0; b < a.n_blocks; ++b) {
             const unsigned long long i0 = (unsigned long long)b * a.block_reads;
             const unsigned nb = (unsigned)min((unsigned long long)a.block_reads, a.N1 - i0);
-            // ---- uniforms of this block (CTA 0) and a copy of z for roll-backs (everyone)
-            if (cta == 0) {
-                unsigned done = 0;
-                while (done < nb) {
-                    if (mt_idx_s >= 624) {   // uniform across the CTA: mt_idx_s only changes between barriers
-                        mt_regenerate_cta(mt);
-                        if (tid == 0) mt_idx_s = 0;
-                        __syncthreads();
-                    }
-                    const int idx = mt_idx_s;
-                    const unsigned take = min((unsigned)(624 - idx), nb - done);
-                    for (unsigned k = tid; k < take; k += kPThreads) __stcg(ublk + done + k, mt_temper(mt.mt[idx + k]));
-                    __syncthreads();
-                    if (tid == 0) mt_idx_s = idx + (int)take;
-                    __syncthreads();
-                    done += take;
-                }
-            }
+            // ---- uniforms of this block (warp 0 of CTA 0: warp-synchronous regeneration is several times faster than a
+            //      CTA-wide one, whose __syncthreads dominate) and a copy of z for roll-backs (everyone else meanwhile)
+            long long tk0 = clock64();
+            // uniforms: warp 0 of CTA 0 is the chain's generator and runs one block ahead of the workers (the very
+            // first block is produced here, every later one during the previous block's first pass)
+            unsigned* ucur = a.ublk + ((size_t)chain * 2 + (gblock & 1u)) * a.block_reads;
+            unsigned* unext = a.ublk + ((size_t)chain * 2 + ((gblock + 1u) & 1u)) * a.block_reads;
+            if (gblock == 0 && cta == 0 && tid < 32) fill_uniforms(mt, mt_idx_s, ucur, nb, tid);
             if (use_counts)
-                for (unsigned k = ctid; k < nb; k += chain_threads) st_cg(zsave + k, ld_cg(z + i0 + k));
+                for (unsigned k = ctid; k < nb; k += chain_threads) st_cg(zsave + k, ld_cg(z + i0 + k));  // slot order
             if (cta == 0 && tid == 0) { sy->flip[0] = 0xffffffffu; sy->flip[1] = 0xffffffffu; }
+            long long tk1 = clock64();
             chain_barrier(sy, n_ctas);
+            long long tk2 = clock64();
+            if (cta == 0 && tid == 0) { sy->prof[0] += tk1 - tk0; sy->prof[1] += tk2 - tk1; }
 
             unsigned long long lo = i0;   // first position that still has to be (re)drawn
             const int s0 = a.blk_seg[b], s1 = a.blk_seg[b + 1];
             for (;;) {
                 const int c0 = ld_cg(counts);   // snapshot of the noise count, valid for every position >= lo
                 unsigned* flip = &sy->flip[flip_parity];
-                for (int sgm = s0 + (int)ctid; sgm < s1; sgm += (int)chain_threads) {
-                    for (int q = a.seg_start[sgm]; q < a.seg_start[sgm + 1]; ++q) {
-                        const unsigned long long i = (unsigned long long)a.order[q];
-                        if (i < lo) continue;
-                        const unsigned long long fr = a.row_ptr[i];
-                        const unsigned len = (unsigned)(a.row_ptr[i + 1] - fr);
-                        int zo = 0;
-                        if (use_counts) {
-                            zo = ld_cg(z + i);
-                            if (zo == 0) atomicSub(counts, 1); else st_cg(counts + zo, ld_cg(counts + zo) - 1);
+                const long long tp0 = clock64();
+                if (is_gen) {   // next block's uniforms, once per block (not on redo passes)
+                    if (lo == i0) {
+                        const bool last = round == a.burnin + chainlen && b == a.n_blocks - 1;
+                        if (!last) {
+                            const int bn = b + 1 < a.n_blocks ? b + 1 : 0;
+                            const unsigned long long in0 = (unsigned long long)bn * a.block_reads;
+                            fill_uniforms(mt, mt_idx_s, unext, (unsigned)min((unsigned long long)a.block_reads, a.N1 - in0), tid);
                         }
-                        const int l = draw_one(a, counts, fr, len, use_counts, c0 - (use_counts && zo == 0 ? 1 : 0),
-                                               __ldcg(ublk + (i - i0)), &sy->err);
-                        const int zn = a.sid[fr + l];
-                        st_cg(z + i, zn);
-                        if (zn == 0) atomicAdd(counts, 1); else st_cg(counts + zn, ld_cg(counts + zn) + 1);
-                        if (use_counts && ((zo == 0) != (zn == 0))) atomicMin(flip, (unsigned)(i - i0));
+                    }
+                } else
+                for (int sgm = s0 + (int)wid; sgm < s1; sgm += (int)n_workers) {
+                    const int q_end = a.seg_start[sgm + 1];
+                    int q = a.seg_start[sgm];
+                    RowRegs nxt;
+                    load_row(a, z, ucur, i0, q, use_counts, nxt);
+                    for (; q < q_end; ++q) {
+                        const RowRegs cur = nxt;
+                        if (q + 1 < q_end) load_row(a, z, ucur, i0, q + 1, use_counts, nxt);   // in flight while `cur` is drawn
+                        if ((unsigned long long)cur.i < lo) continue;
+                        const int zn = draw_row(a, counts, cur, use_counts, c0, &sy->err);
+                        st_cg(z + q, zn);
+                        if (use_counts && ((cur.zo == 0) != (zn == 0))) atomicMin(flip, (unsigned)((unsigned long long)cur.i - i0));
                     }
                 }
+                const long long tp1 = clock64();
                 chain_barrier(sy, n_ctas);
+                if (cta == 0 && tid == 0) { sy->prof[2] += tp1 - tp0; sy->prof[3] += clock64() - tp1; }
                 const unsigned p = *((volatile unsigned*)flip);
                 if (p == 0xffffffffu) break;
                 // ---- roll back everything after position p of the block, then redo it with the corrected c0
                 const unsigned long long redo = i0 + p + 1;
-                for (int sgm = s0 + (int)ctid; sgm < s1; sgm += (int)chain_threads) {
+                if (!is_gen)
+                for (int sgm = s0 + (int)wid; sgm < s1; sgm += (int)n_workers) {
                     for (int q = a.seg_start[sgm]; q < a.seg_start[sgm + 1]; ++q) {
                         const unsigned long long i = (unsigned long long)a.order[q];
                         if (i < redo || i < lo) continue;
-                        const int zn = ld_cg(z + i), zo = ld_cg(zsave + (i - i0));
+                        const int zn = ld_cg(z + q), zo = ld_cg(zsave + ((unsigned long long)q - i0));
                         if (zn == 0) atomicSub(counts, 1); else st_cg(counts + zn, ld_cg(counts + zn) - 1);
                         if (zo == 0) atomicAdd(counts, 1); else st_cg(counts + zo, ld_cg(counts + zo) + 1);
-                        st_cg(z + i, zo);
+                        st_cg(z + q, zo);
                     }
                 }
                 if (cta == 0 && tid == 0) sy->flip[flip_parity ^ 1u] = 0xffffffffu;
@@ -451,7 +598,7 @@ __global__ void __launch_bounds__(kPThreads) gibbs_parallel_kernel(const PArgs a
                 chain_barrier(sy, n_ctas);
                 if (lo >= i0 + nb) break;
             }
-            // leave both flip slots clean for the next block (done at its start)
+            ++gblock;
         }
         if (round > a.burnin && (round - a.burnin - 1) % a.gap == 0) {   // Gibbs.cpp:313-346, by CTA 0 of the chain
             if (cta == 0) {
@@ -604,6 +751,15 @@ static int gibbs_run_serial(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p, r
 }
 
 
+__global__ void permute_rows_kernel(const unsigned long long* row_ptr, const double* conprb, const int* order,
+                                    const unsigned long long* p_off, unsigned long long N1, double* p_con) {
+    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < N1;
+         q += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long src = row_ptr[order[q]], dst = p_off[q], n = p_off[q + 1] - dst;
+        for (unsigned long long k = 0; k < n; ++k) p_con[dst + k] = conprb[src + k];
+    }
+}
+
 // ---- static preparation for the component-parallel sampler (host) ---------------------------------------------
 int gibbs_prepare(rsem_b200_ctx* c, const uint64_t* row_ptr, const int32_t* sid) {
     DevGibbs& g = c->gibbs;
@@ -664,10 +820,33 @@ int gibbs_prepare(rsem_b200_ctx* c, const uint64_t* row_ptr, const int32_t* sid)
     g.block_reads = B;
     g.n_blocks = n_blocks;
     g.n_segs = (int32_t)seg_start.size() - 1;
-    RB_CUDA(cudaMalloc(&g.order, N1 * sizeof(int32_t)));
+    // rows re-laid in slot order so that a segment is one contiguous stream
+    {
+        const uint64_t E = row_ptr[N1];
+        std::vector<uint64_t> p_off(N1 + 1);
+        std::vector<int32_t> p_sid(E);
+        p_off[0] = 0;
+        for (uint64_t q = 0; q < N1; ++q) p_off[q + 1] = p_off[q] + (row_ptr[order[q] + 1] - row_ptr[order[q]]);
+        for (uint64_t q = 0; q < N1; ++q) {
+            const uint64_t src = row_ptr[order[q]], n = row_ptr[order[q] + 1] - src;
+            memcpy(p_sid.data() + p_off[q], sid + src, n * sizeof(int32_t));
+        }
+        RB_CUDA(cudaMalloc(&g.p_off, (N1 + 1) * sizeof(uint64_t)));
+        RB_CUDA(cudaMalloc(&g.p_sid, (E + 16) * sizeof(int32_t)));
+        RB_CUDA(cudaMalloc(&g.p_con, (E + 16) * sizeof(double)));
+        RB_CUDA(cudaMemcpyAsync(g.p_off, p_off.data(), (N1 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        RB_CUDA(cudaMemcpyAsync(g.p_sid, p_sid.data(), E * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        // conprb is permuted on the device from the already uploaded copy
+        RB_CUDA(cudaMalloc(&g.order, N1 * sizeof(int32_t)));
+        RB_CUDA(cudaMemcpyAsync(g.order, order.data(), N1 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        permute_rows_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(reinterpret_cast<const unsigned long long*>(g.row_ptr), g.conprb,
+                                                                   g.order, reinterpret_cast<const unsigned long long*>(g.p_off), N1, g.p_con);
+        RB_CUDA(cudaGetLastError());
+        c->launches++;
+        RB_CUDA(cudaStreamSynchronize(c->stream));
+    }
     RB_CUDA(cudaMalloc(&g.seg_start, seg_start.size() * sizeof(int32_t)));
     RB_CUDA(cudaMalloc(&g.blk_seg, blk_seg.size() * sizeof(int32_t)));
-    RB_CUDA(cudaMemcpyAsync(g.order, order.data(), N1 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     RB_CUDA(cudaMemcpyAsync(g.seg_start, seg_start.data(), seg_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     RB_CUDA(cudaMemcpyAsync(g.blk_seg, blk_seg.data(), blk_seg.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));
@@ -686,6 +865,7 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
     a.N1 = g.N1;
     a.row_ptr = reinterpret_cast<const unsigned long long*>(g.row_ptr);
     a.sid = g.sid; a.conprb = g.conprb; a.order = g.order; a.seg_start = g.seg_start; a.blk_seg = g.blk_seg;
+    a.p_off = reinterpret_cast<const unsigned long long*>(g.p_off); a.p_sid = g.p_sid; a.p_con = g.p_con;
     a.block_reads = g.block_reads; a.n_blocks = g.n_blocks;
     a.M = p->M; a.burnin = p->burnin; a.gap = p->gap; a.n_genes = p->n_genes; a.n_chains = nc;
     a.n0 = p->n0; a.totc = p->totc;
@@ -714,7 +894,7 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
     RB_TRYC(cudaMalloc(&d_counts, (size_t)nc * M1 * sizeof(int)));
     RB_TRYC(cudaMalloc(&d_z, std::max<size_t>((size_t)nc * g.N1, 1) * sizeof(int)));
     RB_TRYC(cudaMalloc(&d_zsave, (size_t)nc * g.block_reads * sizeof(int)));
-    RB_TRYC(cudaMalloc(&d_u, (size_t)nc * g.block_reads * sizeof(unsigned)));
+    RB_TRYC(cudaMalloc(&d_u, (size_t)nc * 2 * g.block_reads * sizeof(unsigned)));
     RB_TRYC(cudaMalloc(&d_sync, (size_t)nc * sizeof(ChainSync)));
     RB_TRYC(cudaMalloc(&d_cv, std::max<size_t>((size_t)total_samples * M1, 1) * sizeof(int)));
     RB_TRYC(cudaMalloc(&d_acc, (size_t)nc * acc_per * sizeof(double)));
@@ -750,6 +930,9 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
     cleanup();
 #undef RB_TRY
 #undef RB_TRYC
+    if (getenv("RSEM_B200_TIMING"))
+        fprintf(stderr, "gibbs chain 0, CTA 0 thread 0 cycles: rng %llu, copy %llu(incl. barrier wait), pass %llu, pass-barrier wait %llu\n",
+                h_sync[0].prof[0], h_sync[0].prof[1], h_sync[0].prof[2], h_sync[0].prof[3]);
     for (int t = 0; t < nc; ++t)
         if (h_sync[t].err) {
             set_error("gibbs: categorical draw fell off the cumulative array (reference: assert(l < len), sampling.h:62)");

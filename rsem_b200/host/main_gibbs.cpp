@@ -9,7 +9,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <ctime>
+#include <future>
 #include <set>
 
 #include "host.hpp"
@@ -118,6 +120,19 @@ int main(int argc, char* argv[]) {
     }
     if (nThreads < 1) nThreads = 1;
 
+    // CUDA context creation takes seconds on a multi-GPU node: overlap it with the .ofg parsing
+    struct CtxResult { int rc; rsem_b200_ctx* ctx; std::string err; };
+    std::future<CtxResult> ctx_future = std::async(std::launch::async, []() {
+        CtxResult r{0, nullptr, ""};
+        const char* dev = getenv("RSEM_B200_DEVICE");
+        r.rc = rsem_b200_ctx_create(dev ? atoi(dev) : 0, &r.ctx);
+        if (r.rc != 0) r.err = rsem_b200_last_error();
+        return r;
+    });
+    const bool timing = getenv("RSEM_B200_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+
     // load_data
     RefData refs;
     load_refs(refName + ".seq", false, refs);
@@ -196,9 +211,14 @@ int main(int argc, char* argv[]) {
     if (g_verbose) printf("Initialization finished!\n");
 
     rsem_b200_ctx* ctx = nullptr;
-    const char* dev = getenv("RSEM_B200_DEVICE");
-    check_rc(rsem_b200_ctx_create(dev ? atoi(dev) : 0, &ctx), "ctx_create");
+    {
+        CtxResult r = ctx_future.get();
+        if (r.rc != 0) die("rsem_b200: ctx_create failed: " + r.err);
+        ctx = r.ctx;
+    }
+    const double t_loaded = now();
     check_rc(rsem_b200_gibbs_upload(ctx, N1, sid.size(), M, row_ptr.data(), sid.data(), conprb.data()), "gibbs_upload");
+    const double t_uploaded = now();
 
     rsem_b200_gibbs_params gp;
     memset(&gp, 0, sizeof gp);
@@ -220,6 +240,9 @@ int main(int argc, char* argv[]) {
     go.sum_c = sum_c.data(); go.sum_c2 = sum_c2.data(); go.sum_tpm = sum_tpm.data(); go.sum_fpkm = sum_fpkm.data();
     go.sum_gene_c2 = sum_g2.data();
     check_rc(rsem_b200_gibbs_run(ctx, &gp, &go), "gibbs_run");
+    if (timing)
+        fprintf(stderr, "rsem-run-gibbs timing: load+ctx %.3f s, upload+components %.3f s, sampling %.3f s (%d chains)\n",
+                t_loaded - t_begin, t_uploaded - t_loaded, now() - t_uploaded, nThreads);
     rsem_b200_ctx_destroy(ctx);
 
     // imd.countvectors<t> (Gibbs.cpp:257-262)

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gibbs_gpu.py tests/test_dropin_gpu.py -m gpu -q -x --timeout 300 -k "gibbs or chains" 2>&1 | tail -5 > gpurun_out/r16_tests.log
+timeout 1500 python tools/bench_gibbs.py --N1 1000000 --M 50000 --burnin 50 --nsamples 64 --chains 8 > gpurun_out/r16_gibbs_1m.log 2>&1
+timeout 1500 python tools/bench_gibbs.py --N1 1000000 --M 50000 --burnin 200 --nsamples 8 --chains 1 > gpurun_out/r16_gibbs_1m_1chain.log 2>&1
+RSEM_B200_GIBBS_BLOCK=4096 timeout 1500 python tools/bench_gibbs.py --N1 1000000 --M 50000 --burnin 50 --nsamples 64 --chains 8 > gpurun_out/r16_gibbs_1m_b4k.log 2>&1
