@@ -2,16 +2,31 @@
 // hand-rolled tokenizer (the reference uses istream >>, 6e6 hits/s).
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <thread>
 
 #include "host.hpp"
 
 namespace host {
 
 bool g_verbose = true;
+int g_io_threads = 1;
+
+void parallel_ranges(size_t n, int parts, const std::function<void(size_t, size_t, int)>& fn) {
+    if (parts < 1) parts = 1;
+    if ((size_t)parts > n) parts = n ? (int)n : 1;
+    if (parts == 1) { fn(0, n, 0); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < parts; ++t) {
+        const size_t b = n * (size_t)t / parts, e = n * (size_t)(t + 1) / parts;
+        pool.emplace_back([&fn, b, e, t]() { fn(b, e, t); });
+    }
+    for (auto& th : pool) th.join();
+}
 
 void die(const std::string& msg) {
     fprintf(stderr, "%s\n", msg.c_str());
@@ -248,11 +263,18 @@ bool single_lq(const char* s, int len, bool has_polyA, int seed_len) {
 }
 }  // namespace
 
-void parse_reads(const std::string& imd, int tag, int read_type, bool has_polyA, int seed_len, ReadStore* keep,
-                 ReadVisitor* visit) {
+// Whole read set -> ReadStore, split over g_io_threads:
+//   1. newline index of every file (per-chunk counts, prefix sum, fill);
+//   2. a record is 4 (FASTQ) / 2 (FASTA) lines; lengths -> offsets by prefix sum;
+//   3. records converted in parallel straight into their final slots.
+// `short_names` receives the first 50 names of reads dropped for length < seed length (the reference warns about
+// those), `n_short` their total number.
+void parse_reads(const std::string& imd, int tag, int read_type, bool has_polyA, int seed_len, ReadStore& out,
+                 std::vector<std::string>* short_names, uint64_t* n_short) {
     init_codes();
     const int s = read_type >= 2 ? 2 : 1;
     const bool hasq = read_type & 1;
+    const int lpr = hasq ? 4 : 2;
     std::vector<std::string> files;
     read_type_files(imd, tag, read_type, files);
     std::vector<char> buf[2];
@@ -261,85 +283,112 @@ void parse_reads(const std::string& imd, int tag, int read_type, bool has_polyA,
         if (!f) { fprintf(stderr, "Cannot open %s! It may not exist.\n", files[m].c_str()); exit(-1); }
         fclose(f);
         buf[m] = slurp(files[m]);
+        if (!buf[m].empty() && buf[m].back() != '\n') buf[m].push_back('\n');
     }
-    Cursor cur[2] = {Cursor(buf[0]), Cursor(buf[s - 1])};
-    if (keep) {
-        keep->n_mates = s;
-        keep->has_qual = hasq;
-        keep->n = 0;
-        for (int m = 0; m < 2; ++m) { keep->off[m].assign(1, 0); keep->base[m].clear(); keep->qual[m].clear(); }
-        keep->lowq.clear();
-        for (int m = 0; m < s; ++m) { keep->base[m].reserve(buf[m].size() / (hasq ? 2 : 1)); }
+    // line starts
+    std::vector<size_t> line[2];
+    for (int m = 0; m < s; ++m) {
+        const char* base = buf[m].data();
+        const size_t n = buf[m].size();
+        const int T = std::max(1, std::min(g_io_threads, (int)(n >> 20) + 1));
+        std::vector<size_t> cnt(T + 1, 0);
+        parallel_ranges(n, T, [&](size_t b, size_t e, int t) {
+            size_t c = 0;
+            for (const char* q = base + b; (q = (const char*)memchr(q, '\n', (size_t)(base + e - q))) != nullptr; ++q) ++c;
+            cnt[t + 1] = c;
+        });
+        for (int t = 0; t < T; ++t) cnt[t + 1] += cnt[t];
+        line[m].resize(cnt[T] + 1);
+        line[m][0] = 0;
+        parallel_ranges(n, T, [&](size_t b, size_t e, int t) {
+            size_t at = cnt[t] + 1;
+            for (const char* q = base + b; (q = (const char*)memchr(q, '\n', (size_t)(base + e - q))) != nullptr; ++q)
+                line[m][at++] = (size_t)(q - base) + 1;
+        });
     }
-    std::vector<uint8_t> tb[2], tq[2];
-    std::string name;
-    for (;;) {
-        const char* seqp[2] = {nullptr, nullptr};
-        const char* qualp[2] = {nullptr, nullptr};
-        int len[2] = {0, 0};
-        bool ok = true;
-        for (int m = 0; m < s && ok; ++m) {
-            const char* b; size_t n;
-            if (!cur[m].line(b, n)) { ok = false; break; }
-            if (n == 0 && cur[m].p >= cur[m].end) { ok = false; break; }
-            if (n == 0 || b[0] != (hasq ? '@' : '>')) {
-                fprintf(stderr, hasq ? "Read file does not look like a FASTQ file!\n" : "Read file does not look like a FASTA file!");
-                exit(-1);
-            }
-            if (m == 0) name.assign(b + 1, n - 1);
-            if (!cur[m].line(b, n)) { ok = false; break; }
-            while (n > 0 && b[n - 1] == '\r') --n;
-            seqp[m] = b; len[m] = (int)n;
-            if (hasq) {
-                if (!cur[m].line(b, n)) { ok = false; break; }
-                if (n == 0 || b[0] != '+') { fprintf(stderr, "Read file does not look like a FASTQ file!\n"); exit(-1); }
-                if (!cur[m].line(b, n)) { ok = false; break; }
-                while (n > 0 && b[n - 1] == '\r') --n;
-                qualp[m] = b;
-                if ((int)n != len[m]) die("Read " + name + " has a different number of bases and quality values!");
-            }
-        }
-        if (!ok) break;
-        bool lq;
-        if (s == 1) lq = seed_len > 0 ? single_lq(seqp[0], len[0], has_polyA, seed_len) : false;
-        else if (seed_len <= 0) lq = false;
-        else if (len[0] < seed_len || len[1] < seed_len) lq = true;  // PairedEndReadQ.h:58-65
-        else lq = single_lq(seqp[0], len[0], has_polyA, seed_len) && single_lq(seqp[1], len[1], has_polyA, seed_len);
-        for (int m = 0; m < s; ++m) {
-            tb[m].resize(len[m]);
-            tq[m].resize(hasq ? len[m] : 0);
-            for (int k = 0; k < len[m]; ++k) {
-                int8_t code = g_code[(unsigned char)seqp[m][k]];
-                if (code < 0) {
-                    if (!lq) { fprintf(stderr, "Found unknown sequence letter %c at function get_base_id!\n", seqp[m][k]); exit(-1); }
-                    code = 4;
-                }
-                tb[m][k] = (uint8_t)code;
-                if (hasq) {
-                    const int q = (unsigned char)qualp[m][k];
-                    if (q < 33 || q > 126) die("Read " + name + " has a quality character outside [33, 126]!");
-                    tq[m][k] = (uint8_t)(q - 33);
-                }
-            }
-        }
-        if (visit) {
-            const uint8_t* bp[2] = {tb[0].data(), tb[1].data()};
-            const uint8_t* qp[2] = {hasq ? tq[0].data() : nullptr, hasq ? tq[1].data() : nullptr};
-            visit->read(lq, s, bp, qp, len, name);
-        }
-        if (keep) {
+    uint64_t n_rec = (line[0].size() - 1) / lpr;
+    if (s == 2) n_rec = std::min<uint64_t>(n_rec, (line[1].size() - 1) / lpr);
+    out = ReadStore();
+    out.n_mates = s;
+    out.has_qual = hasq;
+    out.n = n_rec;
+    out.lowq.assign(n_rec, 0);
+    auto seq_of = [&](int m, uint64_t r, const char*& p, int& len) {
+        const size_t a = line[m][r * lpr + 1], b = line[m][r * lpr + 2];
+        p = buf[m].data() + a;
+        len = (int)(b - a - 1);
+        while (len > 0 && p[len - 1] == '\r') --len;
+    };
+    for (int m = 0; m < s; ++m) {
+        out.off[m].assign(n_rec + 1, 0);
+        parallel_ranges((size_t)n_rec, g_io_threads, [&](size_t b, size_t e, int) {
+            for (size_t r = b; r < e; ++r) { const char* p; int len; seq_of(m, r, p, len); out.off[m][r + 1] = (uint64_t)len; }
+        });
+        for (uint64_t r = 0; r < n_rec; ++r) out.off[m][r + 1] += out.off[m][r];
+        out.base[m].resize(out.off[m][n_rec]);
+        if (hasq) out.qual[m].resize(out.off[m][n_rec]);
+    }
+    const int T = std::max(1, std::min<int>(g_io_threads, (int)(n_rec / 4096) + 1));
+    std::vector<std::vector<std::string>> shorts(T);
+    std::vector<uint64_t> short_cnt(T, 0);
+    std::vector<std::string> errors(T);
+    parallel_ranges((size_t)n_rec, T, [&](size_t rb, size_t re, int t) {
+        for (size_t r = rb; r < re; ++r) {
+            const char* sp[2] = {nullptr, nullptr};
+            int len[2] = {0, 0};
             for (int m = 0; m < s; ++m) {
-                keep->base[m].insert(keep->base[m].end(), tb[m].begin(), tb[m].end());
-                if (hasq) keep->qual[m].insert(keep->qual[m].end(), tq[m].begin(), tq[m].end());
-                keep->off[m].push_back(keep->base[m].size());
+                const char* hdr = buf[m].data() + line[m][r * lpr];
+                if (*hdr != (hasq ? '@' : '>')) { errors[t] = hasq ? "Read file does not look like a FASTQ file!" : "Read file does not look like a FASTA file!"; return; }
+                seq_of(m, r, sp[m], len[m]);
+                if (hasq && buf[m][line[m][r * lpr + 2]] != '+') { errors[t] = "Read file does not look like a FASTQ file!"; return; }
             }
-            keep->lowq.push_back(lq ? 1 : 0);
-            ++keep->n;
+            bool lq;
+            if (s == 1) lq = seed_len > 0 ? single_lq(sp[0], len[0], has_polyA, seed_len) : false;
+            else if (seed_len <= 0) lq = false;
+            else if (len[0] < seed_len || len[1] < seed_len) lq = true;  // PairedEndReadQ.h:58-65
+            else lq = single_lq(sp[0], len[0], has_polyA, seed_len) && single_lq(sp[1], len[1], has_polyA, seed_len);
+            out.lowq[r] = lq ? 1 : 0;
+            if (lq && short_names && (s == 1 ? len[0] < seed_len : (len[0] < seed_len || len[1] < seed_len))) {
+                const char* hdr = buf[0].data() + line[0][r * lpr];
+                size_t hl = line[0][r * lpr + 1] - line[0][r * lpr] - 1;
+                ++short_cnt[t];
+                if (shorts[t].size() < 50) shorts[t].emplace_back(hdr + 1, hl ? hl - 1 : 0);
+            }
+            for (int m = 0; m < s; ++m) {
+                uint8_t* bd = out.base[m].data() + out.off[m][r];
+                for (int k = 0; k < len[m]; ++k) {
+                    int8_t code = g_code[(unsigned char)sp[m][k]];
+                    if (code < 0) {
+                        if (!lq) { errors[t] = std::string("Found unknown sequence letter ") + sp[m][k] + " at function get_base_id!"; return; }
+                        code = 4;
+                    }
+                    bd[k] = (uint8_t)code;
+                }
+                if (hasq) {
+                    const size_t qa = line[m][r * lpr + 3];
+                    int ql = (int)(line[m][r * lpr + 4] - qa - 1);
+                    const char* qp = buf[m].data() + qa;
+                    while (ql > 0 && qp[ql - 1] == '\r') --ql;
+                    if (ql != len[m]) { errors[t] = "A read has a different number of bases and quality values!"; return; }
+                    uint8_t* qd = out.qual[m].data() + out.off[m][r];
+                    for (int k = 0; k < len[m]; ++k) {
+                        const int q = (unsigned char)qp[k];
+                        if (q < 33 || q > 126) { errors[t] = "A read has a quality character outside [33, 126]!"; return; }
+                        qd[k] = (uint8_t)(q - 33);
+                    }
+                }
+            }
         }
-    }
+    });
+    for (const std::string& e : errors) if (!e.empty()) die(e);
+    if (short_names)
+        for (auto& v : shorts) for (auto& nm : v) if (short_names->size() < 50) short_names->push_back(nm);
+    if (n_short) { *n_short = 0; for (uint64_t c : short_cnt) *n_short += c; }
 }
 
 // ---- imd.dat --------------------------------------------------------------------------------------
+// The body is one line per read: the buffer is cut at newlines into one piece per thread, every piece is tokenised into
+// its own arrays and the pieces are concatenated.
 void load_dat(const std::string& path, int read_type, uint64_t expect_n1, HitStore& h) {
     std::vector<char> buf = slurp(path);
     Cursor c(buf);
@@ -348,25 +397,163 @@ void load_dat(const std::string& path, int read_type, uint64_t expect_n1, HitSto
     if ((uint64_t)n1 != expect_n1) die("Number of alignable reads does not match!");
     if (rt != read_type) die("Data file (.dat) does not have the right read type!");
     const bool paired = read_type >= 2;
-    h.N = (uint64_t)n1;
-    h.H = (uint64_t)nh;
-    h.row_ptr.assign(1, 0);
-    h.row_ptr.reserve(h.N + 1);
-    h.sid.clear(); h.pos.clear(); h.insertL.clear();
-    h.sid.reserve(h.H); h.pos.reserve(h.H);
-    if (paired) h.insertL.reserve(h.H);
-    for (uint64_t i = 0; i < h.N; ++i) {
-        long long k, a, b, l = 0;
-        if (!c.next_i64(k) || k <= 0) die("Cannot read alignments from .dat file!");
-        for (long long j = 0; j < k; ++j) {
-            if (!c.next_i64(a) || !c.next_i64(b) || (paired && !c.next_i64(l))) die("Cannot read alignments from .dat file!");
-            h.sid.push_back((int32_t)a);
-            h.pos.push_back((int32_t)b);
-            if (paired) h.insertL.push_back((int32_t)l);
-        }
-        h.row_ptr.push_back(h.sid.size());
+    const char* body = c.p;
+    const char* end = buf.data() + buf.size();
+    const int T = std::max(1, std::min(g_io_threads, (int)((end - body) / (1 << 20)) + 1));
+    std::vector<const char*> cut(T + 1);
+    cut[0] = body;
+    cut[T] = end;
+    for (int t = 1; t < T; ++t) {
+        const char* q = body + (size_t)(end - body) * t / T;
+        const char* nl = (const char*)memchr(q, '\n', (size_t)(end - q));
+        cut[t] = nl ? nl + 1 : end;
     }
-    h.H = h.sid.size();
+    struct Piece { std::vector<uint64_t> deg; std::vector<int32_t> sid, pos, ins; bool bad = false; };
+    std::vector<Piece> pieces(T);
+    parallel_ranges((size_t)T, T, [&](size_t b, size_t, int) {
+        Piece& pc = pieces[b];
+        Cursor cur(buf);
+        cur.p = cut[b];
+        cur.end = cut[b + 1];
+        long long k, x, y, l = 0;
+        while (cur.next_i64(k)) {
+            if (k <= 0) { pc.bad = true; return; }
+            for (long long j = 0; j < k; ++j) {
+                if (!cur.next_i64(x) || !cur.next_i64(y) || (paired && !cur.next_i64(l))) { pc.bad = true; return; }
+                pc.sid.push_back((int32_t)x);
+                pc.pos.push_back((int32_t)y);
+                if (paired) pc.ins.push_back((int32_t)l);
+            }
+            pc.deg.push_back((uint64_t)k);
+        }
+    });
+    uint64_t N = 0, H = 0;
+    for (auto& pc : pieces) {
+        if (pc.bad) die("Cannot read alignments from .dat file!");
+        N += pc.deg.size();
+        H += pc.sid.size();
+    }
+    if (N != (uint64_t)n1) die("Cannot read alignments from .dat file!");
+    h.N = N;
+    h.H = H;
+    h.row_ptr.resize(N + 1);
+    h.sid.resize(H);
+    h.pos.resize(H);
+    h.insertL.resize(paired ? H : 0);
+    std::vector<uint64_t> n_off(T + 1, 0), h_off(T + 1, 0);
+    for (int t = 0; t < T; ++t) { n_off[t + 1] = n_off[t] + pieces[t].deg.size(); h_off[t + 1] = h_off[t] + pieces[t].sid.size(); }
+    parallel_ranges((size_t)T, T, [&](size_t b, size_t, int) {
+        const Piece& pc = pieces[b];
+        uint64_t at = h_off[b];
+        for (size_t i = 0; i < pc.deg.size(); ++i) { h.row_ptr[n_off[b] + i] = at; at += pc.deg[i]; }
+        if (!pc.sid.empty()) {
+            memcpy(h.sid.data() + h_off[b], pc.sid.data(), pc.sid.size() * sizeof(int32_t));
+            memcpy(h.pos.data() + h_off[b], pc.pos.data(), pc.pos.size() * sizeof(int32_t));
+            if (paired) memcpy(h.insertL.data() + h_off[b], pc.ins.data(), pc.ins.size() * sizeof(int32_t));
+        }
+    });
+    h.row_ptr[N] = H;
+}
+
+// ---- imd.ofg ---------------------------------------------------------------------------------------
+void write_ofg(const std::string& path, int M, uint64_t N0, const HitStore& h, const std::vector<double>& conprb,
+               const std::vector<double>& ncpv) {
+    FILE* fo = fopen(path.c_str(), "w");
+    if (!fo) die("Cannot open " + path + " for writing!");
+    fprintf(fo, "%d %llu\n", M, (unsigned long long)N0);
+    const int T = std::max(1, std::min<int>(g_io_threads, (int)(h.H / 200000) + 1));
+    std::vector<std::string> text(T);
+    parallel_ranges((size_t)h.N, T, [&](size_t b, size_t e, int t) {   // "%.15g" like ostream << setprecision(15)
+        std::string& out = text[t];
+        out.reserve((size_t)((h.row_ptr[e] - h.row_ptr[b]) * 26 + (e - b) * 24));
+        char tmp[64];
+        for (size_t i = b; i < e; ++i) {
+            int tot = 0;
+            if (ncpv[i] >= kEps) { ++tot; out.append(tmp, (size_t)snprintf(tmp, sizeof tmp, "0 %.15g ", ncpv[i])); }
+            for (uint64_t j = h.row_ptr[i]; j < h.row_ptr[i + 1]; ++j)
+                if (conprb[j] >= kEps) { ++tot; out.append(tmp, (size_t)snprintf(tmp, sizeof tmp, "%d %.15g ", abs(h.sid[j]), conprb[j])); }
+            if (tot > 0) out.push_back('\n');
+        }
+    });
+    for (const std::string& piece : text) fwrite(piece.data(), 1, piece.size(), fo);
+    fclose(fo);
+}
+
+void load_ofg(const std::string& path, int M, uint64_t& N0, std::vector<uint64_t>& row_ptr, std::vector<int32_t>& sid,
+              std::vector<double>& conprb) {
+    std::vector<char> buf = slurp(path, false);
+    if (buf.empty()) die("Cannot open " + path + "!");
+    if (buf.back() != '\n') buf.push_back('\n');
+    buf.push_back('\0');
+    const char* p = buf.data();
+    const char* end = p + buf.size() - 1;
+    char* q = nullptr;
+    const long long m = strtoll(p, &q, 10);
+    p = q;
+    N0 = strtoull(p, &q, 10);
+    p = q;
+    if (m != M) die("M in " + path + " is not consistent with the reference!");
+    while (p < end && *p != '\n') ++p;
+    ++p;
+    const char* body = p;
+    const int T = std::max(1, std::min(g_io_threads, (int)((end - body) / (1 << 20)) + 1));
+    std::vector<const char*> cut(T + 1);
+    cut[0] = body;
+    cut[T] = end;
+    for (int t = 1; t < T; ++t) {
+        const char* s0 = body + (size_t)(end - body) * t / T;
+        const char* nl = (const char*)memchr(s0, '\n', (size_t)(end - s0));
+        cut[t] = nl ? nl + 1 : end;
+    }
+    struct Piece { std::vector<uint64_t> deg; std::vector<int32_t> sid; std::vector<double> val; };
+    std::vector<Piece> pieces(T);
+    parallel_ranges((size_t)T, T, [&](size_t b, size_t, int) {   // one row per line (Gibbs.cpp:121-134), empty lines count too
+        Piece& pc = pieces[b];
+        const char* s0 = cut[b];
+        const char* e0 = cut[b + 1];
+        while (s0 < e0) {
+            const char* eol = (const char*)memchr(s0, '\n', (size_t)(e0 - s0));
+            if (!eol) eol = e0;
+            uint64_t n = 0;
+            while (s0 < eol) {
+                while (s0 < eol && (*s0 == ' ' || *s0 == '\t' || *s0 == '\r')) ++s0;
+                if (s0 >= eol) break;
+                char* r = nullptr;
+                const long id = strtol(s0, &r, 10);
+                if (r == s0) break;
+                s0 = r;
+                const double v = strtod(s0, &r);
+                if (r == s0) break;
+                s0 = r;
+                pc.sid.push_back((int32_t)id);
+                pc.val.push_back(v);
+                ++n;
+            }
+            pc.deg.push_back(n);
+            s0 = eol + 1;
+        }
+    });
+    uint64_t N = 0, E = 0;
+    std::vector<uint64_t> n_off(T + 1, 0), e_off(T + 1, 0);
+    for (int t = 0; t < T; ++t) {
+        n_off[t + 1] = n_off[t] + pieces[t].deg.size();
+        e_off[t + 1] = e_off[t] + pieces[t].sid.size();
+    }
+    N = n_off[T];
+    E = e_off[T];
+    row_ptr.resize(N + 1);
+    sid.resize(E);
+    conprb.resize(E);
+    parallel_ranges((size_t)T, T, [&](size_t b, size_t, int) {
+        const Piece& pc = pieces[b];
+        uint64_t at = e_off[b];
+        for (size_t i = 0; i < pc.deg.size(); ++i) { row_ptr[n_off[b] + i] = at; at += pc.deg[i]; }
+        if (!pc.sid.empty()) {
+            memcpy(sid.data() + e_off[b], pc.sid.data(), pc.sid.size() * sizeof(int32_t));
+            memcpy(conprb.data() + e_off[b], pc.val.data(), pc.val.size() * sizeof(double));
+        }
+    });
+    row_ptr[N] = E;
 }
 
 }  // namespace host

@@ -9,6 +9,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,10 @@ constexpr int kOlen = 25;           // utils.h:23 OLEN
 constexpr int kRange = 201;         // utils.h:22 RANGE
 
 extern bool g_verbose;
+extern int g_io_threads;  // host threads used for parsing / formatting (rsem-run-em: -p; RSEM_B200_IO_THREADS overrides)
+
+// fn(begin, end, part) over [0, n) split into `parts` contiguous ranges, one std::thread each
+void parallel_ranges(size_t n, int parts, const std::function<void(size_t, size_t, int)>& fn);
 
 [[noreturn]] void die(const std::string& msg);          // message to stderr, exit(-1) (my_assert.h:34-41)
 void check_rc(int rc, const char* what);                // C-ABI error -> die(rsem_b200_last_error())
@@ -56,16 +61,10 @@ struct ReadStore {
     std::vector<uint8_t> base[2], qual[2];
     std::vector<uint8_t> lowq;
 };
-// Parses a whole read set (tag 0 "un", 1 "alignable", 2 "max"; utils.h:129-149).  calc_lq as
-// SingleReadQ.h:63-95 / PairedEndReadQ.h:58-65.  `keep` = false only streams statistics through `visit`.
-struct ReadVisitor {
-    virtual ~ReadVisitor() {}
-    // called once per read; b/q point at codes of each mate (q null without qualities)
-    virtual void read(bool lowq, int n_mates, const uint8_t* const b[2], const uint8_t* const q[2], const int len[2],
-                      const std::string& name) = 0;
-};
-void parse_reads(const std::string& imd_name, int tag, int read_type, bool has_polyA, int seed_len, ReadStore* keep,
-                 ReadVisitor* visit);
+// Parses a whole read set (tag 0 "un", 1 "alignable", 2 "max"; utils.h:129-149) with g_io_threads threads.
+// calc_lq as SingleReadQ.h:63-95 / PairedEndReadQ.h:58-65.
+void parse_reads(const std::string& imd_name, int tag, int read_type, bool has_polyA, int seed_len, ReadStore& out,
+                 std::vector<std::string>* short_names, uint64_t* n_short);
 
 // ---- hits: imd.dat (HitContainer.h:62-79, parseIt.cpp:197-211) -----------------------------------
 struct HitStore {
@@ -74,6 +73,12 @@ struct HitStore {
     std::vector<int32_t> sid, pos, insertL;
 };
 void load_dat(const std::string& path, int read_type, uint64_t expect_n1, HitStore& out);
+
+// imd.ofg (EM.cpp:435-457 writer, Gibbs.cpp:101-137 reader); both split the rows over g_io_threads
+void write_ofg(const std::string& path, int M, uint64_t N0, const HitStore& h, const std::vector<double>& conprb,
+               const std::vector<double>& ncpv);
+void load_ofg(const std::string& path, int M, uint64_t& N0, std::vector<uint64_t>& row_ptr, std::vector<int32_t>& sid,
+              std::vector<double>& conprb);
 
 // ---- model -------------------------------------------------------------------------------------
 struct LenDistH {  // LenDist.h

@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <ctime>
 #include <future>
 #include <thread>
@@ -49,6 +50,13 @@ void usage() {
     printf("  --append-names: append transcript_name/gene_name when available. (default: off)\n");
     printf("// model parameters should be in imdName.mparams.\n");
     exit(-1);
+}
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+double g_t0 = 0;
+void stamp(const char* what) {   // RSEM_B200_TIMING=1: phase timestamps on stderr
+    static const bool on = getenv("RSEM_B200_TIMING") != nullptr;
+    if (on) fprintf(stderr, "rsem-run-em timing: %8.3f s  %s\n", now_s() - g_t0, what);
 }
 
 int env_int(const char* name, int dflt) {
@@ -84,29 +92,12 @@ std::vector<std::pair<uint64_t, uint64_t>> shard_reads(const std::vector<uint64_
     return out;
 }
 
-// imd.ofg, EM.cpp:435-457: "M N0" then one line per read with >= 1 surviving entry
-void write_ofg(const std::string& path, int M, uint64_t N0, const HitStore& h, const std::vector<double>& conprb,
-               const std::vector<double>& ncpv) {
-    FILE* fo = fopen(path.c_str(), "w");
-    if (!fo) die("Cannot open " + path + " for writing!");
-    static char buf[1 << 20];
-    setvbuf(fo, buf, _IOFBF, sizeof buf);
-    fprintf(fo, "%d %llu\n", M, (unsigned long long)N0);
-    for (uint64_t i = 0; i < h.N; ++i) {
-        int tot = 0;
-        if (ncpv[i] >= kEps) { ++tot; fprintf(fo, "0 %.15g ", ncpv[i]); }
-        for (uint64_t j = h.row_ptr[i]; j < h.row_ptr[i + 1]; ++j)
-            if (conprb[j] >= kEps) { ++tot; fprintf(fo, "%d %.15g ", abs(h.sid[j]), conprb[j]); }
-        if (tot > 0) fputc('\n', fo);
-    }
-    fclose(fo);
-}
-
 }  // namespace
 
 int main(int argc, char* argv[]) {
     if (argc < 6) usage();
     const time_t t_start = time(NULL);
+    g_t0 = now_s();
     Args a;
     a.refName = argv[1];
     a.read_type = atoi(argv[2]);
@@ -124,6 +115,7 @@ int main(int argc, char* argv[]) {
         if (!strcmp(argv[i], "--append-names")) a.appendNames = true;
     }
     if (nThreads <= 0) die("Number of threads should be bigger than 0!");
+    g_io_threads = env_int("RSEM_B200_IO_THREADS", nThreads);   // -p: host threads for parsing / formatting
     if (a.read_type < 0 || a.read_type > 3) { fprintf(stderr, "Unknown Read Type!\n"); exit(-1); }
     if (a.genBam)
         die("rsem-run-em (B200): -b (posterior BAM output) is not implemented; run rsem-calculate-expression with --no-bam-output.");
@@ -142,6 +134,7 @@ int main(int argc, char* argv[]) {
     const int M = refs.M;
     std::vector<TranscriptInfo> transcripts;
     load_transcripts(a.refName + ".ti", transcripts);
+    stamp("refs + transcripts loaded");
 
     uint64_t N0, N1, N2, N_tot;
     {
@@ -178,6 +171,7 @@ int main(int argc, char* argv[]) {
     // ---- init (EM.cpp:97-174): hits from .dat; the GPU holds the whole read range ----
     HitStore hits;
     load_dat(a.imdName + ".dat", a.read_type, N1, hits);
+    stamp(".dat parsed");
     if (g_verbose) {
         printf("Thread 0 : N = %llu, NHit = %llu\n", (unsigned long long)hits.N, (unsigned long long)hits.H);
         printf("EM_init finished!\n");
@@ -193,6 +187,7 @@ int main(int argc, char* argv[]) {
     ReadStore reads;
     model.estimate_from_reads(a.imdName, reads);
     if (reads.n != N1) die("Read indices files do not match!");
+    stamp("reads parsed, initial model estimated");
 
     // ---- device set-up: one worker (host thread + context) per GPU, reads sharded like the reference's threads ----
     std::vector<int> devices;
@@ -250,6 +245,7 @@ int main(int argc, char* argv[]) {
         check_rc(rsem_b200_upload_refs(ctx, M, refs.seq_off.data(), refs.seq.data(), refs.full_len.data(), refs.tot_len.data(),
                                        refs.mask_off.data(), refs.mask_words.data()), "upload_refs");
         check_rc(rsem_b200_set_theta(ctx, theta.data()), "set_theta");
+        if (rank == 0) stamp("context ready, inputs uploaded");
 
         // ---- EM loop (EM.cpp:364-416).  Every rank keeps its own copy of the master model and rebuilds it from the
         // (allreduced, hence identical) statistics: no broadcast is needed.
@@ -298,6 +294,7 @@ int main(int argc, char* argv[]) {
                 keep_going = !stopped;
             }
         }
+        if (rank == 0) stamp("EM loop finished");
         // ---- .ofg inputs (EM.cpp:421-457): calcConProbs when the loop ended inside the model rounds
         if (model_dirty) {
             push_model();
@@ -325,7 +322,9 @@ int main(int argc, char* argv[]) {
     }
     model = final_model;
     if (totNum > 0) fprintf(stderr, "Warning: RSEM reaches %d iterations before meeting the convergence criteria.\n", MAX_ROUND);
+    stamp("final pass done, outputs downloaded");
     if (a.gibbsOut) write_ofg(a.imdName + ".ofg", M, N0, hits, conprb, ncpv);
+    stamp(".ofg written");
     counts[0] += N0;
 
     // ---- .theta (EM.cpp:484-500) ----
@@ -342,6 +341,7 @@ int main(int argc, char* argv[]) {
 
     model.write(a.statName + ".model");
     write_results_em(a.refName, a.imdName, transcripts, theta, eel, counts.data(), a.appendNames);
+    stamp(".theta / .model / result rows written");
 
     const time_t t_end = time(NULL);
     printf("Time Used for EM.cpp : %d h %02d m %02d s\n", int((t_end - t_start) / 3600), int((t_end - t_start) % 3600 / 60), int((t_end - t_start) % 60));

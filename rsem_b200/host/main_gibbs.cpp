@@ -13,6 +13,7 @@
 #include <ctime>
 #include <future>
 #include <set>
+#include <thread>
 
 #include "host.hpp"
 
@@ -45,44 +46,6 @@ struct Mt {
         return y;
     }
 };
-
-// imd.ofg -> CSR (Gibbs.cpp:101-137); N1 = number of lines after the header
-void load_ofg(const std::string& path, int M, uint64_t& N0, std::vector<uint64_t>& row_ptr, std::vector<int32_t>& sid,
-              std::vector<double>& conprb) {
-    std::vector<char> buf = slurp(path, false);
-    if (buf.empty()) die("Cannot open " + path + "!");
-    buf.push_back('\n');
-    const char* p = buf.data();
-    const char* end = p + buf.size();
-    char* q = nullptr;
-    const long long m = strtoll(p, &q, 10);
-    p = q;
-    N0 = strtoull(p, &q, 10);
-    p = q;
-    if (m != M) die("M in " + path + " is not consistent with the reference!");
-    while (p < end && *p != '\n') ++p;
-    ++p;
-    row_ptr.assign(1, 0);
-    while (p < end) {
-        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
-        if (!eol) break;
-        if (eol == p && eol + 1 >= end) break;  // the terminator we appended
-        while (p < eol) {
-            while (p < eol && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
-            if (p >= eol) break;
-            const long s = strtol(p, &q, 10);
-            if (q == p) break;
-            p = q;
-            const double c = strtod(p, &q);
-            if (q == p) break;
-            p = q;
-            sid.push_back((int32_t)s);
-            conprb.push_back(c);
-        }
-        row_ptr.push_back(sid.size());
-        p = eol + 1;
-    }
-}
 
 }  // namespace
 
@@ -119,6 +82,11 @@ int main(int argc, char* argv[]) {
         fprintf(stderr, "Warning: Number of samples is less than number of threads! Change the number of threads to %d!\n", nThreads);
     }
     if (nThreads < 1) nThreads = 1;
+    {   // -p means chains here (as in the reference); file parsing uses the host's cores
+        const char* e = getenv("RSEM_B200_IO_THREADS");
+        const unsigned hw = std::thread::hardware_concurrency();
+        g_io_threads = e ? atoi(e) : (int)std::min<unsigned>(hw ? hw : 1, 32);
+    }
 
     // CUDA context creation takes seconds on a multi-GPU node: overlap it with the .ofg parsing
     struct CtxResult { int rc; rsem_b200_ctx* ctx; std::string err; };

@@ -197,57 +197,73 @@ void HostModel::init_master(int model_type, const ModelParamsH& p, const RefData
 }
 
 // ---- estimateFromReads (SingleQModel.h:283-327, PairedEndQModel.h:241-290) -----------------------------
+// One pass over the un / alignable / max read sets: read (mate) length histogram, QualDist counts, base counts of the
+// unalignable reads.  All of them are integer counts, so per-thread partial sums merge exactly.
 namespace {
-struct EstimateVisitor : ReadVisitor {
-    HostModel* m;
-    int tag = 0;
-    int n_warns = 0;
-    uint64_t cnt = 0;
-    void read(bool lowq, int n_mates, const uint8_t* const b[2], const uint8_t* const q[2], const int len[2],
-              const std::string& name) override {
-        const int seedLen = m->mp.seedLen;
-        if (!lowq) {
-            for (int k = 0; k < n_mates; ++k) {
-                LenDistH& d = (m->paired() || m->has_mld) ? m->mld : m->gld;
-                if (!(len[k] > d.lb && len[k] <= d.ub)) die("Read " + name + " has a length outside the allowed range!");  // LenDist.h:47 assert
-                d.pdf[len[k] - d.lb] += 1.0;
-                if (m->hasq()) {  // QualDist::update, QualDist.h:54-63
-                    m->qd_init[q[k][0]] += 1.0;
-                    for (int i = 1; i < len[k]; ++i) m->qd_tran[(size_t)q[k][i - 1] * 100 + q[k][i]] += 1.0;
-                }
-                if (tag == 0) {  // updateC, Noise(Q)Profile
-                    for (int i = 0; i < len[k]; ++i) m->noise_c[m->hasq() ? (size_t)q[k][i] * 5 + b[k][i] : b[k][i]] += 1.0;
-                }
-            }
-        } else if (n_mates == 1 ? len[0] < seedLen : (len[0] < seedLen || len[1] < seedLen)) {
-            // PairedEndQModel.h:272 never increments n_warns (reference quirk); the other three models do
-            const bool count_it = m->type != 3;
-            if (count_it ? ++n_warns <= 50 : n_warns <= 50) {
-                if (n_mates == 1)
-                    fprintf(stderr, "Warning: Read %s is ignored due to read length (= %d) < seed length (= %d)!\n", name.c_str(), len[0], seedLen);
-                else
-                    fprintf(stderr, "Warning: Read %s is ignored due to at least one of the mates' length < seed length (= %d)!\n", name.c_str(), seedLen);
-            }
-        }
-        ++cnt;
-        if (g_verbose && cnt % 1000000 == 0) printf("%llu READS PROCESSED\n", (unsigned long long)cnt);
-    }
+struct ReadCounts {
+    std::vector<double> len, qd_init, qd_tran, noise_c;
+    bool bad_len = false;
 };
 }  // namespace
 
 void HostModel::estimate_from_reads(const std::string& imd, ReadStore& alignable) {
     LenDistH& d = (paired() || has_mld) ? mld : gld;
     d.zero();
-    EstimateVisitor v;
-    v.m = this;
+    int n_warns = 0;
     for (int tag = 0; tag < 3; ++tag) {
         if (mp.N[tag] == 0) continue;
-        v.tag = tag;
-        v.cnt = 0;
-        parse_reads(imd, tag, type, refs->has_polyA, mp.seedLen, tag == 1 ? &alignable : nullptr, &v);
+        ReadStore local;
+        ReadStore& rs = tag == 1 ? alignable : local;
+        std::vector<std::string> short_names;
+        uint64_t n_short = 0;
+        const int n_warns_before = n_warns;
+        parse_reads(imd, tag, type, refs->has_polyA, mp.seedLen, rs, &short_names, &n_short);
+        const int T = std::max(1, std::min<int>(g_io_threads, (int)(rs.n / 8192) + 1));
+        std::vector<ReadCounts> part(T);
+        parallel_ranges((size_t)rs.n, T, [&](size_t b, size_t e, int t) {
+            ReadCounts& pc = part[t];
+            pc.len.assign(d.span + 1, 0.0);
+            if (hasq()) { pc.qd_init.assign(100, 0.0); pc.qd_tran.assign(100 * 100, 0.0); }
+            if (tag == 0) pc.noise_c.assign(n_noise(), 0.0);
+            for (size_t i = b; i < e; ++i) {
+                if (rs.lowq[i]) continue;
+                for (int k = 0; k < rs.n_mates; ++k) {
+                    const uint64_t o = rs.off[k][i];
+                    const int len = (int)(rs.off[k][i + 1] - o);
+                    if (!(len > d.lb && len <= d.ub)) { pc.bad_len = true; continue; }  // LenDist.h:47 assert
+                    pc.len[len - d.lb] += 1.0;
+                    const uint8_t* bq = rs.base[k].data() + o;
+                    if (hasq()) {  // QualDist::update, QualDist.h:54-63
+                        const uint8_t* q = rs.qual[k].data() + o;
+                        pc.qd_init[q[0]] += 1.0;
+                        for (int j = 1; j < len; ++j) pc.qd_tran[(size_t)q[j - 1] * 100 + q[j]] += 1.0;
+                        if (tag == 0) for (int j = 0; j < len; ++j) pc.noise_c[(size_t)q[j] * 5 + bq[j]] += 1.0;  // updateC
+                    } else if (tag == 0) {
+                        for (int j = 0; j < len; ++j) pc.noise_c[bq[j]] += 1.0;
+                    }
+                }
+            }
+        });
+        for (const ReadCounts& pc : part) {
+            if (pc.bad_len) die("A read has a length outside the allowed range!");
+            for (size_t j = 0; j < pc.len.size(); ++j) d.pdf[j] += pc.len[j];
+            for (size_t j = 0; j < pc.qd_init.size(); ++j) qd_init[j] += pc.qd_init[j];
+            for (size_t j = 0; j < pc.qd_tran.size(); ++j) qd_tran[j] += pc.qd_tran[j];
+            for (size_t j = 0; j < pc.noise_c.size(); ++j) noise_c[j] += pc.noise_c[j];
+        }
+        // The reference prints the first 50 warnings; PairedEndQModel.h:272 never increments n_warns (reference
+        // quirk), so that model warns about every short pair and prints no total.
+        for (const std::string& name : short_names) {
+            if (type != 3 && ++n_warns > 50) break;
+            if (!paired())
+                fprintf(stderr, "Warning: Read %s is ignored due to read length < seed length (= %d)!\n", name.c_str(), mp.seedLen);
+            else
+                fprintf(stderr, "Warning: Read %s is ignored due to at least one of the mates' length < seed length (= %d)!\n", name.c_str(), mp.seedLen);
+        }
+        if (type != 3) n_warns = (int)std::min<uint64_t>((uint64_t)n_warns_before + n_short, 1u << 30);
         if (g_verbose) printf("estimateFromReads, N%d finished.\n", tag);
     }
-    if (v.n_warns > 0) fprintf(stderr, "Warning: There are %d reads ignored in total.\n", v.n_warns);
+    if (n_warns > 0) fprintf(stderr, "Warning: There are %d reads ignored in total.\n", n_warns);
     d.finish();
     if (!paired() && mp.mean >= kEps) {  // SingleQModel.h:318-321
         gld.set_as_normal(mp.mean, mp.sd, std::max(mld.minL(), gld.minL()), gld.maxL());
