@@ -75,6 +75,28 @@ def gen_matrix_torch(torch, dev, N, M, deg, seed):
     return row_ptr, sid, conprb, ncpv, H
 
 
+def sort_rows_torch(torch, row_ptr, sid, conprb, ncpv):
+    """Experiment: rows reordered by their first transcript id (locality of the theta gathers / count reductions)."""
+    N = row_ptr.numel() - 1
+    degs = row_ptr[1:] - row_ptr[:-1]
+    key = sid[row_ptr[:-1]].abs()
+    perm = torch.argsort(key, stable=True)
+    nd = degs[perm]
+    nrp = torch.zeros_like(row_ptr)
+    torch.cumsum(nd, 0, out=nrp[1:])
+    nsid = torch.empty_like(sid)
+    ncon = torch.empty_like(conprb)
+    CH = 5_000_000
+    for a in range(0, N, CH):
+        b = min(N, a + CH)
+        ha, hb = int(nrp[a].item()), int(nrp[b].item())
+        src = torch.repeat_interleave(row_ptr[perm[a:b]] - nrp[a:b], nd[a:b]) + torch.arange(ha, hb, device=sid.device)
+        nsid[ha:hb] = sid[src]
+        ncon[ha:hb] = conprb[src]
+        del src
+    return nrp, nsid, ncon, ncpv[perm].contiguous()
+
+
 class ClockSampler:
     """nvidia-smi sampling during the timed region (B200_PROFILING.md 'clocks' recipe)"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -168,6 +190,8 @@ def run_ours(args):
         N = max(1000, int(N * args.scale))
 
     row_ptr, sid, conprb, ncpv, H = gen_matrix_torch(torch, dev, N, M, deg, seed=1234 + rank)
+    if args.sort_rows:
+        row_ptr, sid, conprb, ncpv = sort_rows_torch(torch, row_ptr, sid, conprb, ncpv)
     n0 = N / 20
     ctx = rsem_b200.Context(local)
     stream = torch.cuda.Stream(device=dev)
@@ -187,7 +211,8 @@ def run_ours(args):
     # host copies for the e2e leg and the CPU baseline sample (before the device tensors are dropped)
     e2e_host = None
     sample = None
-    if True:
+    e2e_err = "skipped (--no-e2e)"
+    if not args.no_e2e:
         try:
             e2e_host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (row_ptr, sid, conprb, ncpv)]
             for h, t in zip(e2e_host, (row_ptr, sid, conprb, ncpv)):
@@ -287,7 +312,7 @@ def run_ours(args):
                "note": "job = upload CSR + conprb from pinned host memory, build tiles, run rounds, read theta back"}
     else:
         e2e = {"value": None, "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "pinned host allocation failed: " + e2e_err}
+               "note": "no end-to-end leg: " + e2e_err}
 
     cpu = None
     if rank == 0 and sample is not None:
@@ -381,6 +406,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="scale the number of reads (debugging only)")
     ap.add_argument("--variant", type=int, default=0, help="E-step kernel variant (0 auto, 1 TMA-staged, 2 direct)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sort-rows", action="store_true", help="experiment: reorder the reads by first transcript id")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel experiments)")
     ap.add_argument("--ref-reads", type=int, default=2_000_000, help="reads in the reference arm's bounded sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
