@@ -34,45 +34,61 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // tile geometry of the TMA-staged kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kThreads = 512;
 constexpr int kStages = 3;
-constexpr int kTileHitCap = 2048;  // max hits a stage can hold (actual tiles hold <= 2046: 1024 16-byte pairs)
-constexpr int kTileRowCap = 512;   // max rows a stage can hold (kThreads / G for the actual G)
-constexpr int kSidElems = kTileHitCap + 8;
-constexpr int kConElems = kTileHitCap + 4;
-constexpr int kRowElems = kTileRowCap + 4;
+constexpr int kEnt = 4;  // hits per thread and tile in the flat phases (independent gathers in flight)
 
-// Static per-tile metadata, built once per upload and streamed with the tile: bit q of `mask` is set iff
-// element q of the tile's pair space (q = tile-local hit index + (first hit index & 1)) starts a row;
-// pre[w] = number of set bits in mask words < w.  row(q) = pre[q / 32] + popc(mask[q / 32] & bits(0..q % 32)) - 1.
-constexpr int kMaskWords = 68;
+// A CTA of T threads works on tiles of <= 4 T - 2 hits and <= T rows; (T, CTAs per SM) = (512, 2), (256, 4) or
+// (128, 8) keep 32 warps per SM and stay below 227 KB of shared memory per SM.
+template <int T>
+struct Geo {
+    static constexpr int kThreads = T;
+    static constexpr int kCtasPerSm = 1024 / T;
+    static constexpr int kHitCap = kEnt * T;
+    static constexpr int kRowCap = T;
+    static constexpr int kSidElems = kHitCap + 8;
+    static constexpr int kConElems = kHitCap + 4;
+    static constexpr int kRowElems = kRowCap + 4;
+    static constexpr int kMaskWords = kHitCap / 32 + 4;
+};
+
+// Static per-tile metadata, built once per upload and streamed with the tile.  Word w describes the elements
+// q = 32 w .. 32 w + 31 of the tile (q = tile-local hit index + (first hit index & 1)): bit b of .x is set iff
+// element 32 w + b starts a row, .y = number of row starts in the words before w, so that
+// row(q) = w.y + popc(w.x & bits(0 .. q % 32)) - 1 with one 8-byte shared-memory load.
+template <int T>
 struct __align__(16) TileMeta {
-    unsigned mask[kMaskWords];
-    unsigned short pre[kMaskWords + 4];
+    uint2 w[Geo<T>::kMaskWords];
 };
-static_assert(sizeof(TileMeta) % 16 == 0, "tile metadata must keep 16 B alignment");
 
+template <int T>
 struct __align__(16) Stage {
-    double con[kConElems];
-    unsigned long long rp[kRowElems];
-    double ncp[kRowElems];
-    int sid[kSidElems];
-    TileMeta meta;
+    double con[Geo<T>::kConElems];
+    unsigned long long rp[Geo<T>::kRowElems];
+    double ncp[Geo<T>::kRowElems];
+    int sid[Geo<T>::kSidElems];
+    TileMeta<T> meta;
 };
-static_assert(sizeof(Stage) % 16 == 0, "stage must keep 16 B alignment");
 
 struct TileDesc {  // written by the producer thread when it issues the tile, read by everyone after the wait
     unsigned long long rs, hs;
     unsigned nr, nh;
 };
 
+template <int T>
 struct SmemLayout {
-    Stage stage[kStages];
+    Stage<T> stage[kStages];
     unsigned long long full_bar[kStages];
     TileDesc desc[kStages];
-    double red[kThreads / 32];
-    double inv[kTileRowCap];  // 1 / row sum of the tile being processed
+    double red[T / 32];
+    double inv[Geo<T>::kRowCap];  // 1 / row sum of the tile being processed
 };
+static_assert(sizeof(Stage<512>) % 16 == 0 && sizeof(Stage<256>) % 16 == 0 && sizeof(Stage<128>) % 16 == 0,
+              "stage must keep 16 B alignment");
+static_assert(sizeof(TileMeta<512>) % 16 == 0 && sizeof(TileMeta<256>) % 16 == 0 && sizeof(TileMeta<128>) % 16 == 0,
+              "tile metadata must keep 16 B alignment");
+static_assert(sizeof(SmemLayout<512>) * 2 <= 227 * 1024 && sizeof(SmemLayout<256>) * 4 <= 227 * 1024 &&
+                  sizeof(SmemLayout<128>) * 8 <= 227 * 1024,
+              "shared memory per SM");
 
 struct EstepArgs {
     const unsigned long long* row_ptr;
@@ -226,7 +242,8 @@ __device__ __forceinline__ void flush_count0(double acc0, double* red_smem, doub
 // ------------------------------------------------------------------------------------------------
 // K2, TMA-staged.  grid = #SMs (persistent), block = kThreads.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage& st, unsigned long long* bar,
+template <int T>
+__device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage<T>& st, unsigned long long* bar,
                                            TileDesc& desc) {
     const unsigned long long rs = a.tile_row[k], re = a.tile_row[k + 1];
     const unsigned long long hs = a.tile_hit[k], he = a.tile_hit[k + 1];
@@ -239,12 +256,12 @@ __device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage
     const unsigned b_con = round16((unsigned)(he - hs2) * 8u);
     const unsigned b_rp = round16((unsigned)(re + 1 - rs2) * 8u);
     const unsigned b_nc = round16((unsigned)(re - rs2) * 8u);
-    mbar_expect_tx(bar, b_sid + b_con + b_rp + b_nc + (unsigned)sizeof(TileMeta));
+    mbar_expect_tx(bar, b_sid + b_con + b_rp + b_nc + (unsigned)sizeof(TileMeta<T>));
     if (b_sid) bulk_load(st.sid, a.sid + hs4, b_sid, bar);
     if (b_con) bulk_load(st.con, a.conprb + hs2, b_con, bar);
     bulk_load(st.rp, a.row_ptr + rs2, b_rp, bar);
     bulk_load(st.ncp, a.ncpv + rs2, b_nc, bar);
-    bulk_load(&st.meta, static_cast<const TileMeta*>(a.tile_meta) + k, (unsigned)sizeof(TileMeta), bar);
+    bulk_load(&st.meta, static_cast<const TileMeta<T>*>(a.tile_meta) + k, (unsigned)sizeof(TileMeta<T>), bar);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,10 +278,11 @@ __device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage
 //      consecutive threads -> consecutive addresses -> few sectors per request - and, for the
 //      posterior variant, a coalesced store.
 // ------------------------------------------------------------------------------------------------
-template <int G, bool WRITE_POST>
-__global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs a) {
+template <int T, int G, bool WRITE_POST>
+__global__ void __launch_bounds__(T, 1024 / T) estep_tma_kernel(const EstepArgs a) {
+    constexpr int kThreads = T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+    SmemLayout<T>& sm = *reinterpret_cast<SmemLayout<T>*>(smem_raw);
     if (*a.done_flag) return;
 
     const int tid = threadIdx.x;
@@ -287,7 +305,6 @@ __global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs 
         }
     }
 
-    constexpr int kEnt = kTileHitCap / kThreads;  // hits per thread and tile (4 independent gathers in flight)
     constexpr int kSlots = 8;                     // hits a lane keeps in registers in phase B
     const int g = tid % G;
     const unsigned row_in_tile = tid / G;
@@ -298,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs 
     for (unsigned k = k_first; k < k_end; k += k_step, ++it) {
         const int s = it % kStages;
         const unsigned parity = (it / kStages) & 1u;
-        Stage& st = sm.stage[s];
+        Stage<T>& st = sm.stage[s];
         mbar_wait(&sm.full_bar[s], parity);
 
         const unsigned long long rs = sm.desc[s].rs, hs = sm.desc[s].hs;
@@ -377,14 +394,14 @@ __global__ void __launch_bounds__(kThreads, 2) estep_tma_kernel(const EstepArgs 
         __syncthreads();
 
         // ---- phase C: weight = product (register) * inv[row]; the row of a hit comes from the static head mask:
-        //      q = hit index + lead, row(q) = pre[q / 32] + popc(mask[q / 32] & bits(0 .. q % 32)) - 1
+        //      q = hit index + lead, row(q) = w[q / 32].y + popc(w[q / 32].x & bits(0 .. q % 32)) - 1
 #pragma unroll
         for (int u = 0; u < kEnt; ++u) {
             const unsigned j = tid + kThreads * u;
             if (j < nh) {
                 const unsigned q = j + con_lead;
-                const unsigned word = st.meta.mask[q >> 5];
-                const unsigned row = (unsigned)st.meta.pre[q >> 5] + __popc(word & (0xffffffffu >> (31u - (q & 31u)))) - 1u;
+                const uint2 mw = st.meta.w[q >> 5];
+                const unsigned row = mw.y + __popc(mw.x & (0xffffffffu >> (31u - (q & 31u)))) - 1u;
                 const double w = f[u] * sm.inv[row];
                 if (w != 0.0) red_add_f64(a.count + t[u], w);
                 if (WRITE_POST) a.post[hs + j] = w;
@@ -647,9 +664,11 @@ __global__ void tile_bounds_kernel(const unsigned long long* row_ptr, unsigned l
     tile_row[k] = lo;
 }
 
-// one block per tile: head-bit mask over the tile's pair space + prefix popcounts (TileMeta)
+// one block per tile: row-start bit mask over the tile's elements + prefix counts (TileMeta)
+template <int T>
 __global__ void tile_meta_kernel(const unsigned long long* row_ptr, const unsigned long long* tile_row,
-                                 const unsigned long long* tile_hit, TileMeta* out) {
+                                 const unsigned long long* tile_hit, TileMeta<T>* out) {
+    constexpr int kMaskWords = Geo<T>::kMaskWords;
     __shared__ unsigned m[kMaskWords];
     const unsigned k = blockIdx.x;
     for (int w = threadIdx.x; w < kMaskWords; w += blockDim.x) m[w] = 0u;
@@ -661,14 +680,12 @@ __global__ void tile_meta_kernel(const unsigned long long* row_ptr, const unsign
         atomicOr(&m[q >> 5], 1u << (q & 31u));
     }
     __syncthreads();
-    for (int w = threadIdx.x; w < kMaskWords; w += blockDim.x) out[k].mask[w] = m[w];
     if (threadIdx.x == 0) {
         unsigned run = 0;
         for (int w = 0; w < kMaskWords; ++w) {
-            out[k].pre[w] = (unsigned short)run;
+            out[k].w[w] = make_uint2(m[w], run);
             run += __popc(m[w]);
         }
-        for (int w = kMaskWords; w < kMaskWords + 4; ++w) out[k].pre[w] = (unsigned short)run;
     }
 }
 
@@ -770,24 +787,33 @@ __global__ void __launch_bounds__(1024) theta_update_kernel(double* count, doubl
     }
 }
 
+template <int T, int G, bool WP>
+int launch_staged(rsem_b200_ctx* ctx, const EstepArgs& a) {
+    auto kern = estep_tma_kernel<T, G, WP>;
+    const size_t smem = sizeof(SmemLayout<T>);
+    RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = ctx->sm_count * Geo<T>::kCtasPerSm;
+    if (grid > a.n_tiles) grid = a.n_tiles ? a.n_tiles : 1;
+    kern<<<grid, T, smem, ctx->stream>>>(a);
+    RB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 template <int G, bool WP>
 int launch_variant(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
     if (tma) {
-        static bool attr_set = false;
-        auto kern = estep_tma_kernel<G, WP>;
-        const size_t smem = sizeof(SmemLayout);
-        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        (void)attr_set;
-        unsigned grid = ctx->sm_count * 2;
-        if (grid > a.n_tiles) grid = a.n_tiles ? a.n_tiles : 1;
-        kern<<<grid, kThreads, smem, ctx->stream>>>(a);
-    } else {
-        auto kern = estep_direct_kernel<G, WP>;
-        unsigned long long rows_per_block = (256 / 32) * (32 / G);
-        unsigned long long want = (a.N + rows_per_block - 1) / rows_per_block;
-        unsigned grid = (unsigned)std::min<unsigned long long>(want ? want : 1, (unsigned long long)ctx->sm_count * 8);
-        kern<<<grid, 256, 0, ctx->stream>>>(a);
+        switch (ctx->cta_threads) {
+            case 128: return launch_staged<128, G, WP>(ctx, a);
+            case 256: return launch_staged<256, G, WP>(ctx, a);
+            default: return launch_staged<512, G, WP>(ctx, a);
+        }
     }
+    auto kern = estep_direct_kernel<G, WP>;
+    unsigned long long rows_per_block = (256 / 32) * (32 / G);
+    unsigned long long want = (a.N + rows_per_block - 1) / rows_per_block;
+    unsigned grid = (unsigned)std::min<unsigned long long>(want ? want : 1, (unsigned long long)ctx->sm_count * 8);
+    kern<<<grid, 256, 0, ctx->stream>>>(a);
     RB_CUDA(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -932,18 +958,33 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
     // staged kernels do not handle them, the direct kernel does
     if (deg_info[1]) return 0;
 
-    // CTA tiles: hits <= W + max_deg, kept within one fully unrolled phase-A pass (4 hits per thread) when rows
-    // are short enough, otherwise within the stage capacity
-    if (ctx->max_deg <= (uint32_t)kTileHitCap / 4) {
-        // hits <= W + max_deg <= 2046, so that the pair space (<= 1 lead-in element + hits, rounded up) has at most
-        // kThreads * 2 pairs: every thread owns exactly two pairs of a tile
-        const unsigned long long W = 4ull * kThreads - 2 - ctx->max_deg;
-        if (int rc = build_tile_set(ctx, W, kTileRowCap, &ctx->tile_row, &ctx->tile_hit, &ctx->n_tiles)) return rc;
+    // CTA tiles of the staged kernel: hits <= W + max_deg <= 4 T - 2, so that every thread owns at most kEnt hits
+    // of a tile (one fully unrolled pass per flat phase) and a lead-in element still fits the mask.
+    // measured on C3: 4.35 ms per round with 256 threads x 4 CTAs per SM, 4.39 with 128 x 8, 4.61 with 512 x 2;
+    // rows longer than 256 hits need the larger geometry
+    ctx->cta_threads = ctx->max_deg <= 256 ? 256 : 512;
+    if (const char* e = getenv("RSEM_B200_CTA_THREADS")) {  // tuning knob
+        const int v = atoi(e);
+        if (v == 128 || v == 256 || v == 512) ctx->cta_threads = v;
+    }
+    const unsigned T = (unsigned)ctx->cta_threads;
+    if (ctx->max_deg <= T) {
+        const unsigned long long W = (unsigned long long)kEnt * T - 2 - ctx->max_deg;
+        if (int rc = build_tile_set(ctx, W, T, &ctx->tile_row, &ctx->tile_hit, &ctx->n_tiles)) return rc;
         if (ctx->n_tiles > 0) {
-            RB_CUDA(cudaMalloc(&ctx->tile_meta, (size_t)ctx->n_tiles * sizeof(TileMeta)));
-            tile_meta_kernel<<<ctx->n_tiles, 64, 0, ctx->stream>>>(
-                reinterpret_cast<const unsigned long long*>(ctx->row_ptr), reinterpret_cast<const unsigned long long*>(ctx->tile_row),
-                reinterpret_cast<const unsigned long long*>(ctx->tile_hit), static_cast<TileMeta*>(ctx->tile_meta));
+            const unsigned long long* rp = reinterpret_cast<const unsigned long long*>(ctx->row_ptr);
+            const unsigned long long* tr = reinterpret_cast<const unsigned long long*>(ctx->tile_row);
+            const unsigned long long* th = reinterpret_cast<const unsigned long long*>(ctx->tile_hit);
+            if (T == 128) {
+                RB_CUDA(cudaMalloc(&ctx->tile_meta, (size_t)ctx->n_tiles * sizeof(TileMeta<128>)));
+                tile_meta_kernel<128><<<ctx->n_tiles, 64, 0, ctx->stream>>>(rp, tr, th, static_cast<TileMeta<128>*>(ctx->tile_meta));
+            } else if (T == 256) {
+                RB_CUDA(cudaMalloc(&ctx->tile_meta, (size_t)ctx->n_tiles * sizeof(TileMeta<256>)));
+                tile_meta_kernel<256><<<ctx->n_tiles, 64, 0, ctx->stream>>>(rp, tr, th, static_cast<TileMeta<256>*>(ctx->tile_meta));
+            } else {
+                RB_CUDA(cudaMalloc(&ctx->tile_meta, (size_t)ctx->n_tiles * sizeof(TileMeta<512>)));
+                tile_meta_kernel<512><<<ctx->n_tiles, 64, 0, ctx->stream>>>(rp, tr, th, static_cast<TileMeta<512>*>(ctx->tile_meta));
+            }
             RB_CUDA(cudaGetLastError());
             ctx->launches++;
             RB_CUDA(cudaStreamSynchronize(ctx->stream));
