@@ -220,7 +220,8 @@ int rsem_b200_estep_timing(rsem_b200_ctx* ctx, double* total_ms, uint64_t* launc
 /* enable per-launch event timing of K2 (off by default: it adds two event records per round)    */
 int rsem_b200_set_profiling(rsem_b200_ctx* ctx, int32_t enabled);
 /* select the E/M kernel variant: 0 = auto, 1 = CTA-staged tiles (TMA), 2 = direct (no smem staging),
- * 3 = warp-pipelined tiles (TMA, no CTA barriers)                                                */
+ * 3 = warp-pipelined tiles (TMA, no CTA barriers), 4 = row groups on CTA-staged tiles (TMA, no CTA
+ * barriers, dynamic row batches)                                                                 */
 int rsem_b200_set_estep_variant(rsem_b200_ctx* ctx, int32_t variant);
 
 #ifdef __cplusplus

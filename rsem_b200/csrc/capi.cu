@@ -589,7 +589,7 @@ int rsem_b200_set_profiling(rsem_b200_ctx* c, int32_t enabled) {
 }
 
 int rsem_b200_set_estep_variant(rsem_b200_ctx* c, int32_t v) {
-    RB_ARG(c && v >= 0 && v <= 3, "variant must be 0..3");
+    RB_ARG(c && v >= 0 && v <= 4, "variant must be 0..4");
     c->variant = v;
     return 0;
 }

@@ -140,6 +140,7 @@ struct rsem_b200_ctx {
     uint32_t n_wtiles = 0;
     int group = 16;       // lanes cooperating on one row (K1 / K3 / direct K2)
     int tma_group = 4;    // lanes per row in phase B of the staged K2
+    int rows_group = 8;   // lanes per row of the row-group K2 (variant 4)
     int cta_threads = 512;  // threads per CTA of the staged K2 (tile geometry depends on it)
     int variant = 0;      // 0 auto, 1 CTA-staged, 2 direct, 3 warp-pipelined
 

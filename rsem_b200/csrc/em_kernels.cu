@@ -242,7 +242,7 @@ __device__ __forceinline__ void flush_count0(double acc0, double* red_smem, doub
 // ------------------------------------------------------------------------------------------------
 // K2, TMA-staged.  grid = #SMs (persistent), block = kThreads.
 // ------------------------------------------------------------------------------------------------
-template <int T>
+template <int T, bool META = true>
 __device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage<T>& st, unsigned long long* bar,
                                            TileDesc& desc) {
     const unsigned long long rs = a.tile_row[k], re = a.tile_row[k + 1];
@@ -256,12 +256,12 @@ __device__ __forceinline__ void issue_tile(const EstepArgs& a, unsigned k, Stage
     const unsigned b_con = round16((unsigned)(he - hs2) * 8u);
     const unsigned b_rp = round16((unsigned)(re + 1 - rs2) * 8u);
     const unsigned b_nc = round16((unsigned)(re - rs2) * 8u);
-    mbar_expect_tx(bar, b_sid + b_con + b_rp + b_nc + (unsigned)sizeof(TileMeta<T>));
+    mbar_expect_tx(bar, b_sid + b_con + b_rp + b_nc + (META ? (unsigned)sizeof(TileMeta<T>) : 0u));
     if (b_sid) bulk_load(st.sid, a.sid + hs4, b_sid, bar);
     if (b_con) bulk_load(st.con, a.conprb + hs2, b_con, bar);
     bulk_load(st.rp, a.row_ptr + rs2, b_rp, bar);
     bulk_load(st.ncp, a.ncpv + rs2, b_nc, bar);
-    bulk_load(&st.meta, static_cast<const TileMeta<T>*>(a.tile_meta) + k, (unsigned)sizeof(TileMeta<T>), bar);
+    if (META) bulk_load(&st.meta, static_cast<const TileMeta<T>*>(a.tile_meta) + k, (unsigned)sizeof(TileMeta<T>), bar);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -414,6 +414,174 @@ __global__ void __launch_bounds__(T, 1024 / T) estep_tma_kernel(const EstepArgs 
             if (kn < k_end) issue_tile(a, (unsigned)kn, st, &sm.full_bar[s], sm.desc[s]);
         }
     }
+    flush_count0(acc0, sm.red, a.count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2, row groups on staged tiles (variant 4).  Same TMA ring as above, but a tile is consumed in ONE pass with
+// no CTA-wide barrier: a warp claims batches of 32 / G rows from a shared-memory counter, G lanes own a row,
+// lane g holds the row's hits g, g + G, ... (kRowSlots of them in registers): ids and conprb come from the stage
+// (each byte of it is read once), theta is gathered, the row sum goes through log2(G) xor-shuffles and the
+// normalised weights leave as red.global.add.f64 - a warp instruction covers 32 / G runs of G adjacent
+// transcripts, which the L2 reduction unit handles as well as 32 consecutive ones.  Two batches are in flight
+// per warp for instruction-level parallelism.  The warp that finishes a tile last refills its stage.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowSlots = 4;
+constexpr int kRowUnroll = 2;
+
+template <int T>
+struct RowSmem {
+    Stage<T> stage[kStages];
+    unsigned long long full_bar[kStages];
+    TileDesc desc[kStages];
+    unsigned int next_batch[kStages];
+    unsigned int warps_done[kStages];
+    double red[T / 32];
+};
+
+template <int T, int G, bool WRITE_POST>
+__global__ void __launch_bounds__(T, 1024 / T) estep_rows_kernel(const EstepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    RowSmem<T>& sm = *reinterpret_cast<RowSmem<T>*>(smem_raw);
+    if (*a.done_flag) return;
+    constexpr unsigned kWarps = T / 32;
+    constexpr unsigned kRowsPerBatch = 32 / G;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&sm.full_bar[s], 1);
+            sm.next_batch[s] = 0;
+            sm.warps_done[s] = 0;
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    unsigned k_first = blockIdx.x, k_end = a.n_tiles, k_step = gridDim.x;
+    if (a.contig) {
+        const unsigned q = a.n_tiles / gridDim.x, r = a.n_tiles % gridDim.x;
+        k_first = blockIdx.x * q + min(blockIdx.x, r);
+        k_end = k_first + q + (blockIdx.x < r ? 1u : 0u);
+        k_step = 1;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            const unsigned k = k_first + s * k_step;
+            if (k < k_end) issue_tile<T, false>(a, k, sm.stage[s], &sm.full_bar[s], sm.desc[s]);
+        }
+    }
+
+    const unsigned g = lane % G;
+    const unsigned row_in_batch = lane / G;
+    const double theta0 = __ldg(a.theta);
+    double acc0 = 0.0;
+
+    unsigned it = 0;
+    for (unsigned k = k_first; k < k_end; k += k_step, ++it) {
+        const int s = it % kStages;
+        const unsigned parity = (it / kStages) & 1u;
+        Stage<T>& st = sm.stage[s];
+        mbar_wait(&sm.full_bar[s], parity);
+
+        const unsigned long long rs = sm.desc[s].rs, hs = sm.desc[s].hs;
+        const unsigned nr = sm.desc[s].nr;
+        const unsigned roff = (unsigned)(rs & 1ull);
+        const int* s_sid = st.sid + (unsigned)(hs & 3ull);
+        const double* s_con = st.con + (unsigned)(hs & 1ull);
+        const unsigned n_batches = (nr + kRowsPerBatch - 1) / kRowsPerBatch;
+
+        for (;;) {
+            unsigned b0 = 0;
+            if (lane == 0) b0 = atomicAdd(&sm.next_batch[s], (unsigned)kRowUnroll);
+            b0 = __shfl_sync(0xffffffffu, b0, 0);
+            if (b0 >= n_batches) break;
+
+            unsigned row[kRowUnroll], hb[kRowUnroll], he[kRowUnroll];
+            bool valid[kRowUnroll];
+            int t[kRowUnroll][kRowSlots];
+            double x[kRowUnroll][kRowSlots];
+            double f0[kRowUnroll], part[kRowUnroll];
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) {
+                row[u] = (b0 + u) * kRowsPerBatch + row_in_batch;
+                valid[u] = row[u] < nr;
+                hb[u] = he[u] = 0;
+                if (valid[u]) {
+                    hb[u] = (unsigned)(st.rp[roff + row[u]] - hs);
+                    he[u] = (unsigned)(st.rp[roff + row[u] + 1] - hs);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u)
+#pragma unroll
+                for (int q = 0; q < kRowSlots; ++q) {
+                    const unsigned j = hb[u] + g + q * G;
+                    t[u][q] = j < he[u] ? s_sid[j] : 0;
+                }
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u)
+#pragma unroll
+                for (int q = 0; q < kRowSlots; ++q) x[u][q] = __ldg(a.theta + t[u][q]);
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) {
+#pragma unroll
+                for (int q = 0; q < kRowSlots; ++q) {
+                    const unsigned j = hb[u] + g + q * G;
+                    const double c = j < he[u] ? s_con[j] : 0.0;
+                    x[u][q] *= c;
+                    if (x[u][q] < kEpsilon) x[u][q] = 0.0;
+                }
+                part[u] = (x[u][0] + x[u][1]) + (x[u][2] + x[u][3]);
+                for (unsigned j = hb[u] + g + kRowSlots * G; j < he[u]; j += G) {  // rows longer than kRowSlots * G
+                    double f = __ldg(a.theta + s_sid[j]) * s_con[j];
+                    if (f < kEpsilon) f = 0.0;
+                    part[u] += f;
+                }
+                f0[u] = 0.0;
+                if (valid[u] && g == 0) {
+                    f0[u] = theta0 * st.ncp[roff + row[u]];
+                    if (f0[u] < kEpsilon) f0[u] = 0.0;
+                    part[u] += f0[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) part[u] = group_sum<G>(part[u]);
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) {
+                const double inv = part[u] >= kEpsilon ? 1.0 / part[u] : 0.0;
+                const double p0 = f0[u] * inv;
+                acc0 += p0;
+                if (WRITE_POST && valid[u] && g == 0) a.post0[rs + row[u]] = p0;
+#pragma unroll
+                for (int q = 0; q < kRowSlots; ++q) {
+                    const unsigned j = hb[u] + g + q * G;
+                    const double w = x[u][q] * inv;
+                    if (w != 0.0) red_add_f64(a.count + t[u][q], w);
+                    if (WRITE_POST && j < he[u]) a.post[hs + j] = w;
+                }
+                for (unsigned j = hb[u] + g + kRowSlots * G; j < he[u]; j += G) {
+                    const int tt = s_sid[j];
+                    double f = __ldg(a.theta + tt) * s_con[j];
+                    if (f < kEpsilon) f = 0.0;
+                    const double w = f * inv;
+                    if (w != 0.0) red_add_f64(a.count + tt, w);
+                    if (WRITE_POST) a.post[hs + j] = w;
+                }
+            }
+        }
+        // this warp has read everything it needs from stage s; the last warp to get here refills the stage
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned old = atomicAdd(&sm.warps_done[s], 1u);
+            if (old == kWarps - 1) {
+                sm.warps_done[s] = 0;
+                sm.next_batch[s] = 0;
+                const unsigned long long kn = (unsigned long long)k + (unsigned long long)kStages * k_step;
+                if (kn < k_end) issue_tile<T, false>(a, (unsigned)kn, st, &sm.full_bar[s], sm.desc[s]);
+            }
+        }
+    }
+    __syncthreads();
     flush_count0(acc0, sm.red, a.count);
 }
 
@@ -800,8 +968,28 @@ int launch_staged(rsem_b200_ctx* ctx, const EstepArgs& a) {
     return 0;
 }
 
+template <int T, int G, bool WP>
+int launch_rows(rsem_b200_ctx* ctx, const EstepArgs& a) {
+    auto kern = estep_rows_kernel<T, G, WP>;
+    const size_t smem = sizeof(RowSmem<T>);
+    RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = ctx->sm_count * Geo<T>::kCtasPerSm;
+    if (grid > a.n_tiles) grid = a.n_tiles ? a.n_tiles : 1;
+    kern<<<grid, T, smem, ctx->stream>>>(a);
+    RB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 template <int G, bool WP>
 int launch_variant(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
+    if (tma && ctx->variant == 4) {
+        switch (ctx->cta_threads) {
+            case 128: return launch_rows<128, G, WP>(ctx, a);
+            case 256: return launch_rows<256, G, WP>(ctx, a);
+            default: return launch_rows<512, G, WP>(ctx, a);
+        }
+    }
     if (tma) {
         switch (ctx->cta_threads) {
             case 128: return launch_staged<128, G, WP>(ctx, a);
@@ -835,7 +1023,7 @@ int launch_warp(rsem_b200_ctx* ctx, const EstepArgs& a) {
 template <bool WP>
 int launch_group(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
     if (tma) {
-        switch (ctx->tma_group) {
+        switch (ctx->variant == 4 ? ctx->rows_group : ctx->tma_group) {
             case 1: return launch_variant<1, WP>(ctx, a, true);
             case 2: return launch_variant<2, WP>(ctx, a, true);
             case 4: return launch_variant<4, WP>(ctx, a, true);
@@ -950,9 +1138,11 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
     ctx->group = mean_deg <= 5.0 ? 4 : mean_deg <= 11.0 ? 8 : mean_deg <= 26.0 ? 16 : 32;
     // lanes per row in phase B of the CTA-staged kernel: about one lane per 5 hits
     ctx->tma_group = mean_deg <= 7.0 ? 1 : mean_deg <= 14.0 ? 2 : mean_deg <= 28.0 ? 4 : mean_deg <= 56.0 ? 8 : mean_deg <= 112.0 ? 16 : 32;
+    // lanes per row of the row-group kernel: kRowSlots hits per lane should cover about 1.5 mean rows
+    ctx->rows_group = mean_deg <= 3.0 ? 1 : mean_deg <= 6.0 ? 2 : mean_deg <= 12.0 ? 4 : mean_deg <= 24.0 ? 8 : mean_deg <= 48.0 ? 16 : 32;
     if (const char* e = getenv("RSEM_B200_GROUP")) {  // tuning knob (profiling only)
         const int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ctx->tma_group = v;
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ctx->tma_group = ctx->rows_group = v;
     }
     // rows without hits are never produced by rsem-parse-alignments (HitContainer.h:67 asserts tot > 0): the
     // staged kernels do not handle them, the direct kernel does
@@ -1025,7 +1215,7 @@ int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
     // 2 direct, 3 warp-pipelined
     const bool use_warp = ctx->n_wtiles > 0 && (ctx->variant == 3 || (ctx->variant == 0 && ctx->n_tiles == 0));
     const bool tma = !use_warp && ctx->n_tiles > 0 && ctx->variant != 2 && ctx->variant != 3;
-    if ((ctx->variant == 1 && ctx->n_tiles == 0) || (ctx->variant == 3 && ctx->n_wtiles == 0)) {
+    if (((ctx->variant == 1 || ctx->variant == 4) && ctx->n_tiles == 0) || (ctx->variant == 3 && ctx->n_wtiles == 0)) {
         set_error("staged E-step requested but the matrix has rows that are empty or too long for a stage");
         return RSEM_B200_ERR_UNSUPPORTED;
     }

@@ -42,7 +42,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("case", CASES)
 def test_em_rounds_match_oracle(ctx, oracle, case, variant):
     N, M, deg, zipf, family, zero_rows = case
@@ -53,7 +53,7 @@ def test_em_rounds_match_oracle(ctx, oracle, case, variant):
     ctx.upload_hits(row_ptr, sid, M)
     ctx.upload_conprb(conprb, ncpv)
     ctx.set_theta(theta0)
-    if zero_rows > 0 and variant in (1, 3):
+    if zero_rows > 0 and variant in (1, 3, 4):
         # rows without hits are legal at the C ABI but never produced by rsem-parse-alignments; only the
         # direct kernel handles them and asking for the staged one must fail loudly
         from rsem_b200 import RsemB200Error
@@ -90,7 +90,7 @@ def test_expected_weights(ctx, oracle):
     row_ptr, sid, conprb, ncpv = synth.random_matrix(8000, 700, 8, seed=9)
     theta = np.random.default_rng(1).random(701)
     theta /= theta.sum()
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         ctx.set_estep_variant(variant)
         ctx.upload_hits(row_ptr, sid, 700)
         ctx.upload_conprb(conprb, ncpv)
