@@ -75,11 +75,12 @@ def gen_matrix_torch(torch, dev, N, M, deg, seed):
     return row_ptr, sid, conprb, ncpv, H
 
 
-def sort_rows_torch(torch, row_ptr, sid, conprb, ncpv):
-    """Experiment: rows reordered by their first transcript id (locality of the theta gathers / count reductions)."""
+def sort_rows_torch(torch, row_ptr, sid, conprb, ncpv, by):
+    """Experiment: rows reordered by their first transcript id (locality of the theta gathers / count reductions)
+    or by their degree (uniform row batches)."""
     N = row_ptr.numel() - 1
     degs = row_ptr[1:] - row_ptr[:-1]
-    key = sid[row_ptr[:-1]].abs()
+    key = sid[row_ptr[:-1]].abs() if by == "start" else degs
     perm = torch.argsort(key, stable=True)
     nd = degs[perm]
     nrp = torch.zeros_like(row_ptr)
@@ -191,7 +192,7 @@ def run_ours(args):
 
     row_ptr, sid, conprb, ncpv, H = gen_matrix_torch(torch, dev, N, M, deg, seed=1234 + rank)
     if args.sort_rows:
-        row_ptr, sid, conprb, ncpv = sort_rows_torch(torch, row_ptr, sid, conprb, ncpv)
+        row_ptr, sid, conprb, ncpv = sort_rows_torch(torch, row_ptr, sid, conprb, ncpv, args.sort_rows)
     n0 = N / 20
     ctx = rsem_b200.Context(local)
     stream = torch.cuda.Stream(device=dev)
@@ -406,7 +407,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="scale the number of reads (debugging only)")
     ap.add_argument("--variant", type=int, default=0, help="E-step kernel variant (0 auto, 1 TMA-staged, 2 direct)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sort-rows", action="store_true", help="experiment: reorder the reads by first transcript id")
+    ap.add_argument("--sort-rows", default="", choices=["", "start", "deg"],
+                    help="experiment: reorder the reads by first transcript id or by degree")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel experiments)")
     ap.add_argument("--ref-reads", type=int, default=2_000_000, help="reads in the reference arm's bounded sample")
     args = ap.parse_args()

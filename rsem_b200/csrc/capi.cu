@@ -38,6 +38,7 @@ void free_hits(rsem_b200_ctx* c) {
     dev_free(c, &c->ncpv, c->N);
     if (c->post) dev_free(c, &c->post, c->H);
     if (c->post0) dev_free(c, &c->post0, c->N);
+    if (c->theta_tex) { cudaDestroyTextureObject(c->theta_tex); c->theta_tex = 0; c->theta_tex_ptr = nullptr; }
     if (c->theta) dev_free(c, &c->theta, (size_t)c->M + 1);
     if (c->count) dev_free(c, &c->count, (size_t)c->M + 1);
     if (c->tile_row) { cudaFree(c->tile_row); c->tile_row = nullptr; }

@@ -141,11 +141,14 @@ struct rsem_b200_ctx {
     int group = 16;       // lanes cooperating on one row (K1 / K3 / direct K2)
     int tma_group = 4;    // lanes per row in phase B of the staged K2
     int rows_group = 8;   // lanes per row of the row-group K2 (variant 4)
+    bool tiles_for_rows = true;  // tiles built for the row-group kernel (no row-start masks) or for the three-phase one
     int cta_threads = 512;  // threads per CTA of the staged K2 (tile geometry depends on it)
     int variant = 0;      // 0 auto, 1 CTA-staged, 2 direct, 3 warp-pipelined
 
     // EM state
     double* theta = nullptr;   // M + 1
+    cudaTextureObject_t theta_tex = 0;  // optional texture view of theta (em_kernels.cu)
+    const double* theta_tex_ptr = nullptr;
     double* count = nullptr;   // M + 1
     int* done_flag = nullptr;  // device int: 1 once the loop condition ended the run
     int* err_flag = nullptr;

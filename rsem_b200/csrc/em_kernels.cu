@@ -86,6 +86,7 @@ static_assert(sizeof(Stage<512>) % 16 == 0 && sizeof(Stage<256>) % 16 == 0 && si
               "stage must keep 16 B alignment");
 static_assert(sizeof(TileMeta<512>) % 16 == 0 && sizeof(TileMeta<256>) % 16 == 0 && sizeof(TileMeta<128>) % 16 == 0,
               "tile metadata must keep 16 B alignment");
+static_assert(sizeof(Stage<1024>) * kStages + 4096 <= 227 * 1024, "shared memory per SM");
 static_assert(sizeof(SmemLayout<512>) * 2 <= 227 * 1024 && sizeof(SmemLayout<256>) * 4 <= 227 * 1024 &&
                   sizeof(SmemLayout<128>) * 8 <= 227 * 1024,
               "shared memory per SM");
@@ -108,6 +109,7 @@ struct EstepArgs {
     unsigned int n_wtiles;
     unsigned long long N;
     const int* done_flag;
+    cudaTextureObject_t theta_tex;  // theta as a 1-D int2 texture (row-group kernel, optional gather path)
     unsigned int contig;  // 1: a CTA walks a contiguous range of tiles, 0: tiles strided by the grid
 };
 
@@ -145,6 +147,18 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 __device__ __forceinline__ void red_add_f64(double* addr, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+// the same, skipped when v == 0 (no branch: the reduction is predicated)
+__device__ __forceinline__ void red_add_f64_nz(double* addr, double v) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.neu.f64 p, %1, 0d0000000000000000;\n"
+        "@p red.global.add.f64 [%0], %1;\n"
+        "}\n" ::"l"(addr),
+        "d"(v)
+        : "memory");
 }
 
 template <int G>
@@ -427,7 +441,6 @@ __global__ void __launch_bounds__(T, 1024 / T) estep_tma_kernel(const EstepArgs 
 // per warp for instruction-level parallelism.  The warp that finishes a tile last refills its stage.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRowSlots = 4;
-constexpr int kRowUnroll = 2;
 
 template <int T>
 struct RowSmem {
@@ -439,7 +452,13 @@ struct RowSmem {
     double red[T / 32];
 };
 
-template <int T, int G, bool WRITE_POST>
+// theta[i] through the texture pipe instead of the LSU pipe (which is the busiest unit of this kernel)
+__device__ __forceinline__ double theta_fetch(cudaTextureObject_t tex, unsigned i) {
+    const int2 v = tex1Dfetch<int2>(tex, (int)i);
+    return __hiloint2double(v.y, v.x);
+}
+
+template <int T, int G, bool WRITE_POST, int kRowUnroll, bool TEX>
 __global__ void __launch_bounds__(T, 1024 / T) estep_rows_kernel(const EstepArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RowSmem<T>& sm = *reinterpret_cast<RowSmem<T>*>(smem_raw);
@@ -521,7 +540,8 @@ __global__ void __launch_bounds__(T, 1024 / T) estep_rows_kernel(const EstepArgs
 #pragma unroll
             for (int u = 0; u < kRowUnroll; ++u)
 #pragma unroll
-                for (int q = 0; q < kRowSlots; ++q) x[u][q] = __ldg(a.theta + t[u][q]);
+                for (int q = 0; q < kRowSlots; ++q)
+                    x[u][q] = TEX ? theta_fetch(a.theta_tex, (unsigned)t[u][q]) : __ldg(a.theta + t[u][q]);
 #pragma unroll
             for (int u = 0; u < kRowUnroll; ++u) {
 #pragma unroll
@@ -968,9 +988,9 @@ int launch_staged(rsem_b200_ctx* ctx, const EstepArgs& a) {
     return 0;
 }
 
-template <int T, int G, bool WP>
-int launch_rows(rsem_b200_ctx* ctx, const EstepArgs& a) {
-    auto kern = estep_rows_kernel<T, G, WP>;
+template <int T, int G, bool WP, bool TEX>
+int launch_rows_tex(rsem_b200_ctx* ctx, const EstepArgs& a) {
+    auto kern = estep_rows_kernel<T, G, WP, 2, TEX>;
     const size_t smem = sizeof(RowSmem<T>);
     RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = ctx->sm_count * Geo<T>::kCtasPerSm;
@@ -981,12 +1001,18 @@ int launch_rows(rsem_b200_ctx* ctx, const EstepArgs& a) {
     return 0;
 }
 
+template <int T, int G, bool WP>
+int launch_rows(rsem_b200_ctx* ctx, const EstepArgs& a) {
+    return a.theta_tex ? launch_rows_tex<T, G, WP, true>(ctx, a) : launch_rows_tex<T, G, WP, false>(ctx, a);
+}
+
 template <int G, bool WP>
 int launch_variant(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
-    if (tma && ctx->variant == 4) {
+    if (tma && ctx->tiles_for_rows) {
         switch (ctx->cta_threads) {
             case 128: return launch_rows<128, G, WP>(ctx, a);
             case 256: return launch_rows<256, G, WP>(ctx, a);
+            case 1024: return launch_rows<1024, G, WP>(ctx, a);
             default: return launch_rows<512, G, WP>(ctx, a);
         }
     }
@@ -1023,7 +1049,7 @@ int launch_warp(rsem_b200_ctx* ctx, const EstepArgs& a) {
 template <bool WP>
 int launch_group(rsem_b200_ctx* ctx, const EstepArgs& a, bool tma) {
     if (tma) {
-        switch (ctx->variant == 4 ? ctx->rows_group : ctx->tma_group) {
+        switch (ctx->tiles_for_rows ? ctx->rows_group : ctx->tma_group) {
             case 1: return launch_variant<1, WP>(ctx, a, true);
             case 2: return launch_variant<2, WP>(ctx, a, true);
             case 4: return launch_variant<4, WP>(ctx, a, true);
@@ -1150,12 +1176,15 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
 
     // CTA tiles of the staged kernel: hits <= W + max_deg <= 4 T - 2, so that every thread owns at most kEnt hits
     // of a tile (one fully unrolled pass per flat phase) and a lead-in element still fits the mask.
-    // measured on C3: 4.35 ms per round with 256 threads x 4 CTAs per SM, 4.39 with 128 x 8, 4.61 with 512 x 2;
-    // rows longer than 256 hits need the larger geometry
-    ctx->cta_threads = ctx->max_deg <= 256 ? 256 : 512;
+    // Tile geometry follows the kernel that will consume the tiles.  Measured on C3 (ms per round):
+    //   row-group kernel (variants 0 / 4): 3.40 with 1024 threads x 1 CTA per SM, 3.50 with 512 x 2, 3.75 with 256 x 4
+    //   three-phase kernel (variant 1):    4.35 with 256 x 4, 4.39 with 128 x 8, 4.61 with 512 x 2
+    ctx->tiles_for_rows = ctx->variant == 0 || ctx->variant == 4;
+    if (ctx->tiles_for_rows) ctx->cta_threads = 1024;
+    else ctx->cta_threads = ctx->max_deg <= 256 ? 256 : 512;
     if (const char* e = getenv("RSEM_B200_CTA_THREADS")) {  // tuning knob
         const int v = atoi(e);
-        if (v == 128 || v == 256 || v == 512) ctx->cta_threads = v;
+        if (v == 128 || v == 256 || v == 512 || (v == 1024 && ctx->tiles_for_rows)) ctx->cta_threads = v;
     }
     const unsigned T = (unsigned)ctx->cta_threads;
     if (ctx->max_deg <= T) {
@@ -1165,7 +1194,9 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
             const unsigned long long* rp = reinterpret_cast<const unsigned long long*>(ctx->row_ptr);
             const unsigned long long* tr = reinterpret_cast<const unsigned long long*>(ctx->tile_row);
             const unsigned long long* th = reinterpret_cast<const unsigned long long*>(ctx->tile_hit);
-            if (T == 128) {
+            if (ctx->tiles_for_rows) {
+                // the row-group kernel needs no row-start masks
+            } else if (T == 128) {
                 RB_CUDA(cudaMalloc(&ctx->tile_meta, (size_t)ctx->n_tiles * sizeof(TileMeta<128>)));
                 tile_meta_kernel<128><<<ctx->n_tiles, 64, 0, ctx->stream>>>(rp, tr, th, static_cast<TileMeta<128>*>(ctx->tile_meta));
             } else if (T == 256) {
@@ -1210,9 +1241,39 @@ int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
     // each CTA walks a contiguous range of tiles (4 % faster on C3 than striding by the grid); 0 = strided
     static const int tile_order = getenv("RSEM_B200_TILE_ORDER") ? atoi(getenv("RSEM_B200_TILE_ORDER")) : 1;
     a.contig = tile_order != 0;
+    a.theta_tex = 0;
+    static const int use_tex = getenv("RSEM_B200_THETA_TEX") ? atoi(getenv("RSEM_B200_THETA_TEX")) : 0;
+    if (use_tex) {
+        if (ctx->theta_tex && ctx->theta_tex_ptr != ctx->theta) {
+            cudaDestroyTextureObject(ctx->theta_tex);
+            ctx->theta_tex = 0;
+        }
+        if (!ctx->theta_tex) {
+            cudaResourceDesc rd = {};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = ctx->theta;
+            rd.res.linear.desc = cudaCreateChannelDesc<int2>();
+            rd.res.linear.sizeInBytes = ((size_t)ctx->M + 1) * sizeof(double);
+            cudaTextureDesc td = {};
+            td.readMode = cudaReadModeElementType;
+            RB_CUDA(cudaCreateTextureObject(&ctx->theta_tex, &rd, &td, nullptr));
+            ctx->theta_tex_ptr = ctx->theta;
+        }
+        a.theta_tex = ctx->theta_tex;
+    }
     if (ctx->N == 0) return 0;
-    // variant: 0 auto (CTA-staged > warp-pipelined > direct; measured on C3: 5.9 / 6.4 / 9.3 ms), 1 CTA-staged,
-    // 2 direct, 3 warp-pipelined
+    if (ctx->tiles_for_rows != (ctx->variant == 0 || ctx->variant == 4)) {  // variant changed after the upload
+        if (int rc = em_build_tiles(ctx)) return rc;
+        a.tile_row = reinterpret_cast<const unsigned long long*>(ctx->tile_row);
+        a.tile_hit = reinterpret_cast<const unsigned long long*>(ctx->tile_hit);
+        a.tile_meta = ctx->tile_meta;
+        a.n_tiles = ctx->n_tiles;
+        a.wtile_row = reinterpret_cast<const unsigned long long*>(ctx->wtile_row);
+        a.wtile_hit = reinterpret_cast<const unsigned long long*>(ctx->wtile_hit);
+        a.n_wtiles = ctx->n_wtiles;
+    }
+    // variant: 0 auto (row groups on staged tiles > warp-pipelined > direct), 1 three-phase CTA-staged, 2 direct,
+    // 3 warp-pipelined, 4 row groups on staged tiles
     const bool use_warp = ctx->n_wtiles > 0 && (ctx->variant == 3 || (ctx->variant == 0 && ctx->n_tiles == 0));
     const bool tma = !use_warp && ctx->n_tiles > 0 && ctx->variant != 2 && ctx->variant != 3;
     if (((ctx->variant == 1 || ctx->variant == 4) && ctx->n_tiles == 0) || (ctx->variant == 3 && ctx->n_wtiles == 0)) {

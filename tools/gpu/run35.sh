@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+B="python bench.py --no-cpu-baseline --no-e2e --steps 10 --scale 0.4"
+timeout 300 $B > gpurun_out/r35_base.log 2>&1
+timeout 300 $B --sort-rows deg > gpurun_out/r35_deg.log 2>&1
+for f in base deg; do echo $f; tail -n 1 gpurun_out/r35_$f.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['k2_ms_per_launch'], d['roofline']['frac'])"; done
