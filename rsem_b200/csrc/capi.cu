@@ -120,6 +120,15 @@ void harvest_events(rsem_b200_ctx* ctx) {
             ctx->estep_launches++;
         }
     }
+    if (ctx->ev_used > 1 && getenv("RSEM_B200_TIMING_GAPS")) {  // time between consecutive K2 launches (K4, allreduce, launch gaps)
+        double gap = 0.0;
+        for (size_t i = 0; i + 1 < ctx->ev_used; ++i) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->ev_pool[i].second, ctx->ev_pool[i + 1].first) == cudaSuccess) gap += ms;
+        }
+        fprintf(stderr, "rsem_b200: mean time between K2 launches %.4f ms over %zu gaps\n", gap / (double)(ctx->ev_used - 1),
+                ctx->ev_used - 1);
+    }
     ctx->ev_used = 0;
 }
 

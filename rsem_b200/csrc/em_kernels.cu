@@ -18,6 +18,7 @@
 //
 // Clamp semantics are the reference's: a term < 1e-300 is 0, a row whose sum < 1e-300
 // contributes nothing (EM.cpp:212,219,223).
+#include <cooperative_groups.h>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
 #include <thrust/unique.h>
@@ -909,37 +910,44 @@ __global__ void max_degree_kernel(const unsigned long long* row_ptr, unsigned lo
 // K4: theta update + convergence statistics (EM.cpp:391-416).  The M-vector is tiny (<= 1.6 MB):
 // one CTA, two passes, block reductions.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) theta_update_kernel(double* count, double* theta, int M1, double n0, int round,
-                                                            int min_round, int max_round,
-                                                            rsem_b200_round_stats* stats_slot, int* done_flag,
-                                                            int* err_flag) {
+constexpr int kThetaCluster = 8;  // CTAs of the M-step kernel: one thread-block cluster, partial results through DSMEM
+
+__global__ void __cluster_dims__(kThetaCluster, 1, 1) __launch_bounds__(1024)
+    theta_update_kernel(double* count, double* theta, int M1, double n0, int round, int min_round, int max_round,
+                        rsem_b200_round_stats* stats_slot, int* done_flag, int* err_flag) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ double sh_d[32];
     __shared__ long long sh_l[32];
-    __shared__ double sh_sum;
-    if (*done_flag) return;
+    __shared__ double cl_sum[kThetaCluster];     // every CTA receives every CTA's partial sum
+    __shared__ double cl_b[kThetaCluster];       // rank 0 receives the partial statistics
+    __shared__ long long cl_t[kThetaCluster];
+    if (*done_flag) return;  // same value in every CTA of the cluster
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const unsigned rank = cluster.block_rank();
+    const int first = (int)rank * (int)blockDim.x + tid, step = kThetaCluster * (int)blockDim.x;
 
     double s = 0.0;
-    for (int i = tid; i < M1; i += blockDim.x) s += count[i];
-    if (tid == 0) s += n0;
+    for (int i = first; i < M1; i += step) s += count[i];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) sh_d[warp] = s;
     __syncthreads();
     if (warp == 0) {
         double v = lane < nwarp ? sh_d[lane] : 0.0;
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) sh_sum = v;
+        if (lane < kThetaCluster) *cluster.map_shared_rank(&cl_sum[rank], lane) = v;
     }
-    __syncthreads();
-    const double sum = sh_sum;
+    cluster.sync();
+    double sum = n0;
+    for (int r = 0; r < kThetaCluster; ++r) sum += cl_sum[r];  // same order in every CTA
     if (!(sum >= kEpsilon)) {  // reference: assert(sum >= EPSILON), EM.cpp:397
-        if (tid == 0) { *err_flag = 1; *done_flag = 1; }
+        if (rank == 0 && tid == 0) { *err_flag = 1; *done_flag = 1; }
         return;
     }
 
     double bmax = 0.0;
     long long tot = 0;
-    for (int i = tid; i < M1; i += blockDim.x) {
+    for (int i = first; i < M1; i += step) {
         const double c = count[i] + (i == 0 ? n0 : 0.0);
         const double tn = c / sum;
         const double old = theta[i];
@@ -966,12 +974,20 @@ __global__ void __launch_bounds__(1024) theta_update_kernel(double* count, doubl
             t += __shfl_xor_sync(0xffffffffu, t, o);
         }
         if (lane == 0) {
-            stats_slot->sum = sum;
-            stats_slot->bchange = b;
-            stats_slot->totnum = t;
-            // loop continues while ROUND < MIN_ROUND || (totNum > 0 && ROUND < MAX_ROUND)
-            if (!(round < min_round || (t > 0 && round < max_round))) *done_flag = 1;
+            *cluster.map_shared_rank(&cl_b[rank], 0) = b;
+            *cluster.map_shared_rank(&cl_t[rank], 0) = t;
         }
+    }
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
+        double b = 0.0;
+        long long t = 0;
+        for (int r = 0; r < kThetaCluster; ++r) { b = fmax(b, cl_b[r]); t += cl_t[r]; }
+        stats_slot->sum = sum;
+        stats_slot->bchange = b;
+        stats_slot->totnum = t;
+        // loop continues while ROUND < MIN_ROUND || (totNum > 0 && ROUND < MAX_ROUND)
+        if (!(round < min_round || (t > 0 && round < max_round))) *done_flag = 1;
     }
 }
 
@@ -1303,7 +1319,7 @@ int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
 }
 
 int em_launch_theta_update(rsem_b200_ctx* ctx, double n0, int round, int min_round, int max_round, int stats_slot) {
-    theta_update_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->count, ctx->theta, ctx->M + 1, n0, round, min_round,
+    theta_update_kernel<<<kThetaCluster, 1024, 0, ctx->stream>>>(ctx->count, ctx->theta, ctx->M + 1, n0, round, min_round,
                                                      max_round, ctx->d_stats + stats_slot, ctx->done_flag,
                                                      ctx->err_flag);
     RB_CUDA(cudaGetLastError());

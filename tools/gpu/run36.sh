@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_em_kernels_gpu.py -m gpu -q -x --timeout 600 2>&1 | tail -3 > gpurun_out/r36_tests.log
+cat gpurun_out/r36_tests.log
+B="python bench.py --no-cpu-baseline --no-e2e --steps 20"
+timeout 300 $B > gpurun_out/r36_c3.log 2>&1
+timeout 300 $B --workload C1 > gpurun_out/r36_c1.log 2>&1
+timeout 300 $B --workload C2 > gpurun_out/r36_c2.log 2>&1
+for f in c3 c1 c2; do echo $f; tail -n 1 gpurun_out/r36_$f.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['k2_ms_per_launch'], d['roofline']['frac'])"; done
