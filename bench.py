@@ -99,8 +99,10 @@ def sort_rows_torch(torch, row_ptr, sid, conprb, ncpv, by):
 
 
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md 'clocks' recipe)"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling while the GPU runs the timed workload (B200_PROFILING.md 'clocks' recipe).
+    nvidia-smi needs ~0.2 s to start and samples every 100 ms, so it is started before the warm-up and only
+    samples whose time stamp lies inside [t0, t1] (GPU under the benchmark's load) are used."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -114,31 +116,52 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def _rows(self):
+        out = []
+        try:
+            with open(self.f.name) as f:
+                for line in f:
+                    c = [x.strip() for x in line.split(",")]
+                    if len(c) < 10:
+                        continue
+                    try:
+                        ts = time.mktime(time.strptime(c[0].split(".")[0], "%Y/%m/%d %H:%M:%S")) + float("0." + c[0].split(".")[1])
+                        out.append((ts, float(c[2]), float(c[3]), c[6:10]))
+                    except (ValueError, IndexError):
+                        continue
+        except Exception:
+            pass
+        return out
+
+    def wait_first(self, timeout=3.0):
+        t = time.time()
+        while self.p and time.time() - t < timeout and not self._rows():
+            time.sleep(0.05)
+
+    def count_since(self, t0):
+        return sum(1 for r in self._rows() if r[0] >= t0)
+
+    def stop(self, t0, t1):
         if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.12)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
         self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f:
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+        rows = [r for r in self._rows() if t0 <= r[0] <= t1 + 0.05]
+        os.unlink(self.f.name)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.f.name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[2] for r in rows) if rows else None,
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed region + identical rounds right after it (nvidia-smi -lms 100)"}
 
 
 def measured_peak_gbs():
@@ -236,21 +259,31 @@ def run_ours(args):
 
     # ---- warm-up + timed region (device-resident inputs) ------------------------------------------
     BIG = 1 << 30
-    ctx.em_rounds(12, args.warmup, BIG, BIG, n0)
     sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first()
+    ctx.em_rounds(12, args.warmup, BIG, BIG, n0)
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    if rank == 0:
-        sampler.start()
+    t_load0 = time.time()
     with torch.cuda.stream(stream):
         e0.record(stream)
         stats, _ = ctx.em_rounds(12 + args.warmup, args.steps, BIG, BIG, n0)
         e1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
+    # keep the same load running until nvidia-smi has a few samples of it (a 20-round region lasts 70 ms)
+    extra = 0
+    while world == 1 and sampler.count_since(t_load0) < 5 and time.time() - t_load0 < 2.5:
+        ctx.em_rounds(12 + args.warmup + args.steps + extra, 20, BIG, BIG, n0)
+        extra += 20
+    if world > 1:  # every rank must take part in the allreduce of each round: a fixed continuation
+        ctx.em_rounds(12 + args.warmup + args.steps, 200, BIG, BIG, n0)
+    t_load1 = time.time()
+    clocks = sampler.stop(t_load0, t_load1) if rank == 0 else None
+    ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -271,7 +304,7 @@ def run_ours(args):
     ab = alg_bytes(N, H, M)
     achieved = ab / (k2_ms / k2_n * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "estep_tma_kernel (K2)",
+                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "estep_rows_kernel (K2)",
                 "algorithmic_bytes_per_launch": ab, "k2_ms_per_launch": round(k2_ms / k2_n, 4), "peak_source": peak_src}
     try:
         with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:

@@ -11,10 +11,14 @@
 //     tiles through a 3-stage shared-memory ring filled by 1-D bulk-async copies (TMA,
 //     cp.async.bulk + mbarrier complete_tx), so the bytes in flight per SM are set by the ring
 //     depth, not by occupancy or by the dependent row_ptr -> hits -> theta load chain;
-//   * products theta * conprb and the count updates are computed flat over hits (thread = hit), row
-//     sums by small lane groups (G ~ degree / 5) with xor-shuffles; normalised weights go to the
-//     count vector with red.global.add.f64 (L2-resident), the noise entry count[0] - which every row
-//     touches - is privatised in a register and flushed once per CTA.
+//   * default kernel (estep_rows_kernel): warps claim batches of rows from a shared-memory counter, G lanes
+//     own a row with its products in registers, row sums by xor-shuffles, normalised weights go to the
+//     count vector with red.global.add.f64 (L2-resident); no CTA-wide barrier per tile, the warp that finishes a
+//     tile last refills its stage.  The noise entry count[0] - which every row touches - is privatised in a
+//     register and flushed once per CTA;
+//   * alternatives kept for comparison and as fallbacks: three CTA-wide flat phases per tile (estep_tma_kernel),
+//     warp-private tiles (estep_warp_kernel), no staging (estep_direct_kernel);
+//   * the M-step is one 8-CTA thread-block cluster exchanging partial sums through distributed shared memory.
 //
 // Clamp semantics are the reference's: a term < 1e-300 is 0, a row whose sum < 1e-300
 // contributes nothing (EM.cpp:212,219,223).
