@@ -338,6 +338,7 @@ int rsem_b200_upload_reads(rsem_b200_ctx* c, int32_t n_mates, const uint64_t* of
     for (int m = 0; m < n_mates; ++m) {
         const uint64_t total = offs[m][N];
         for (uint64_t i = 0; i < N; ++i) max_len = std::max<int>(max_len, (int)(offs[m][i + 1] - offs[m][i]));
+        c->reads.total_bases[m] = total;
         RB_CUDA(cudaMalloc(&c->reads.off[m], (N + 1) * sizeof(uint64_t)));
         RB_CUDA(cudaMalloc(&c->reads.base[m], total + 16));
         RB_CUDA(cudaMemcpyAsync(c->reads.off[m], offs[m], (N + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
@@ -352,6 +353,7 @@ int rsem_b200_upload_reads(rsem_b200_ctx* c, int32_t n_mates, const uint64_t* of
     c->reads.n_mates = n_mates;
     c->reads.has_qual = qual1 != nullptr;
     c->reads.max_len = max_len;
+    c->reads.qmax = -1;
     RB_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }

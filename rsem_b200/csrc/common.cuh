@@ -76,6 +76,8 @@ struct DevReads {
     uint8_t* qual[2] = {nullptr, nullptr};
     uint8_t* lowq = nullptr;
     int max_len = 0;
+    int qmax = -1;                          // largest quality value (computed on first use)
+    unsigned long long total_bases[2] = {0, 0};
 };
 
 struct DevRefs {

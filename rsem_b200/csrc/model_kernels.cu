@@ -17,6 +17,8 @@
 // kReplicas copies of the statistics block (the ~20 hot (quality, base, base) cells would
 // otherwise serialise in one L2 slice) which a second kernel folds into copy 0.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -57,6 +59,7 @@ struct ModelArgs {
     size_t o_noise, o_gld, o_rspd;  // offsets inside a block (profile at 0)
     int gld_lb, gld_span;
     int prof_rows_smem;     // rows of the profile table staged in shared memory (0 = use global)
+    int q_rows;             // quality models: (largest quality value in the read set) + 1
     int* err_flag;
 };
 
@@ -83,7 +86,57 @@ __device__ __forceinline__ bool ref_mask(const ModelArgs& a, int sid, int p) {
     return (a.mask_words[a.mask_off[sid] + (p >> 5)] >> (p & 31)) & 1u;
 }
 
-// product over the bases of one mate of p[row][ref][read]; row = quality (Q models) or position
+// Byte streams through aligned 8-byte loads: a lane walks 50-150 consecutive bytes of a read, its qualities and a
+// transcript; LDG.U8 per base made the LSU pipe the limiter (3 scattered byte loads per lane and base), one LDG.64
+// per 8 bases and stream does not.  The arrays carry >= 16 bytes of tail padding (capi.cu).
+struct FwdBytes {  // bytes p[0], p[1], ... 8 at a time
+    const unsigned long long* q;
+    unsigned long long cur, nxt;
+    unsigned sh;
+    __device__ __forceinline__ explicit FwdBytes(const unsigned char* p, bool active = true) {
+        q = reinterpret_cast<const unsigned long long*>(reinterpret_cast<unsigned long long>(p) & ~7ull);
+        sh = (unsigned)(reinterpret_cast<unsigned long long>(p) & 7ull) * 8u;
+        cur = nxt = 0ull;
+        if (active) {
+            cur = __ldg(q);
+            nxt = __ldg(q + 1);
+        }
+    }
+    // the next 8 bytes (byte k of the stream chunk in bits 8k..8k+7); `more` = another chunk will be asked for
+    __device__ __forceinline__ unsigned long long next(bool more) {
+        const unsigned long long v = sh ? (cur >> sh) | (nxt << (64u - sh)) : cur;
+        ++q;
+        cur = nxt;
+        if (more) nxt = __ldg(q + 1);
+        return v;
+    }
+};
+struct RevBytes {  // bytes p[0], p[-1], p[-2], ... 8 at a time; never loads below `floor`
+    const unsigned long long* q;
+    const unsigned long long* floor;
+    unsigned long long lo, hi;
+    unsigned sh;
+    __device__ __forceinline__ RevBytes(const unsigned char* p, const unsigned char* base) {
+        const unsigned long long a = reinterpret_cast<unsigned long long>(p) - 7ull;
+        q = reinterpret_cast<const unsigned long long*>(a & ~7ull);
+        floor = reinterpret_cast<const unsigned long long*>(base);
+        sh = (unsigned)(a & 7ull) * 8u;
+        lo = q >= floor ? __ldg(q) : 0ull;
+        hi = __ldg(q + 1);
+    }
+    // 8 bytes p[-8c-7 .. -8c]: byte p[-8c-k] sits in bits 8(7-k)..8(7-k)+7
+    __device__ __forceinline__ unsigned long long next(bool more) {
+        const unsigned long long v = sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+        --q;
+        hi = lo;
+        if (more) lo = q >= floor ? __ldg(q) : 0ull;
+        return v;
+    }
+};
+__device__ __forceinline__ unsigned byte_of(unsigned long long w, int k) { return (unsigned)(w >> (8 * k)) & 0xffu; }
+
+// product over the bases of one mate of p[row][ref][read]; row = quality (Q models) or position.
+// Multiplication order = base order, as in the reference.
 template <bool HASQ>
 __device__ __forceinline__ double seq_prob(const ModelArgs& a, const double* prof, int mate, unsigned long long i,
                                            int sid, int pos, int dir) {
@@ -94,20 +147,39 @@ __device__ __forceinline__ double seq_prob(const ModelArgs& a, const double* pro
         *a.err_flag = 2;
         return 0.0;
     }
-    const unsigned char* rb = a.rbase[mate] + o;
-    const unsigned char* rq = HASQ ? a.rqual[mate] + o : nullptr;
+    if (len <= 0) return 1.0;
+    FwdBytes rb(a.rbase[mate] + o);
+    FwdBytes rq(HASQ ? a.rqual[mate] + o : a.rbase[mate] + o, HASQ);
     const unsigned char* s = a.seq + a.seq_off[sid] + (dir == 0 ? pos : totLen - 1 - pos);
     double prob = 1.0;
     if (dir == 0) {
-        for (int k = 0; k < len; ++k) {
-            const int row = HASQ ? rq[k] : k;
-            prob *= prof[(row * 5 + s[k]) * 5 + rb[k]];
+        FwdBytes sb(s);
+        for (int k0 = 0; k0 < len; k0 += 8) {
+            const bool more = k0 + 8 < len;
+            const unsigned long long ws = sb.next(more), wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
+            const int n = min(8, len - k0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < n) {
+                    const int row = HASQ ? (int)byte_of(wq, k) : k0 + k;
+                    prob *= prof[(row * 5 + (int)byte_of(ws, k)) * 5 + (int)byte_of(wr, k)];
+                }
+            }
         }
     } else {
-        for (int k = 0; k < len; ++k) {
-            const int c = s[-k];
-            const int row = HASQ ? rq[k] : k;
-            prob *= prof[(row * 5 + (c < 4 ? 3 - c : 4)) * 5 + rb[k]];
+        RevBytes sb(s, a.seq);
+        for (int k0 = 0; k0 < len; k0 += 8) {
+            const bool more = k0 + 8 < len;
+            const unsigned long long ws = sb.next(more), wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
+            const int n = min(8, len - k0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < n) {
+                    const int c = (int)byte_of(ws, 7 - k);
+                    const int row = HASQ ? (int)byte_of(wq, k) : k0 + k;
+                    prob *= prof[(row * 5 + (c < 4 ? 3 - c : 4)) * 5 + (int)byte_of(wr, k)];
+                }
+            }
         }
     }
     return prob;
@@ -117,10 +189,18 @@ template <bool HASQ>
 __device__ __forceinline__ double noise_prob(const ModelArgs& a, const double* nprof, int mate, unsigned long long i) {
     const unsigned long long o = a.roff[mate][i];
     const int len = (int)(a.roff[mate][i + 1] - o);
-    const unsigned char* rb = a.rbase[mate] + o;
-    const unsigned char* rq = HASQ ? a.rqual[mate] + o : nullptr;
+    if (len <= 0) return 1.0;
+    FwdBytes rb(a.rbase[mate] + o);
+    FwdBytes rq(HASQ ? a.rqual[mate] + o : a.rbase[mate] + o, HASQ);
     double prob = 1.0;
-    for (int k = 0; k < len; ++k) prob *= HASQ ? nprof[rq[k] * 5 + rb[k]] : nprof[rb[k]];
+    for (int k0 = 0; k0 < len; k0 += 8) {
+        const bool more = k0 + 8 < len;
+        const unsigned long long wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
+        const int n = min(8, len - k0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < n) prob *= HASQ ? nprof[byte_of(wq, k) * 5 + byte_of(wr, k)] : nprof[byte_of(wr, k)];
+    }
     return prob;
 }
 
@@ -239,15 +319,39 @@ __device__ __forceinline__ void prof_update(const ModelArgs& a, double* tab, int
     const unsigned long long o = a.roff[mate][i];
     const int len = (int)(a.roff[mate][i + 1] - o);
     const int totLen = a.tot_len[sid];
-    if (pos < 0 || pos + len > totLen) return;
-    const unsigned char* rb = a.rbase[mate] + o;
-    const unsigned char* rq = HASQ ? a.rqual[mate] + o : nullptr;
+    if (pos < 0 || pos + len > totLen || len <= 0) return;
+    FwdBytes rb(a.rbase[mate] + o);
+    FwdBytes rq(HASQ ? a.rqual[mate] + o : a.rbase[mate] + o, HASQ);
     const unsigned char* s = a.seq + a.seq_off[sid] + (dir == 0 ? pos : totLen - 1 - pos);
-    for (int k = 0; k < len; ++k) {
-        int c = dir == 0 ? s[k] : s[-k];
-        if (dir) c = c < 4 ? 3 - c : 4;
-        const int row = HASQ ? rq[k] : k;
-        red_add(tab + (row * 5 + c) * 5 + rb[k], frac);
+    if (dir == 0) {
+        FwdBytes sb(s);
+        for (int k0 = 0; k0 < len; k0 += 8) {
+            const bool more = k0 + 8 < len;
+            const unsigned long long ws = sb.next(more), wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
+            const int n = min(8, len - k0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < n) {
+                    const int row = HASQ ? (int)byte_of(wq, k) : k0 + k;
+                    red_add(tab + (row * 5 + (int)byte_of(ws, k)) * 5 + (int)byte_of(wr, k), frac);
+                }
+            }
+        }
+    } else {
+        RevBytes sb(s, a.seq);
+        for (int k0 = 0; k0 < len; k0 += 8) {
+            const bool more = k0 + 8 < len;
+            const unsigned long long ws = sb.next(more), wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
+            const int n = min(8, len - k0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < n) {
+                    const int c = (int)byte_of(ws, 7 - k);
+                    const int row = HASQ ? (int)byte_of(wq, k) : k0 + k;
+                    red_add(tab + (row * 5 + (c < 4 ? 3 - c : 4)) * 5 + (int)byte_of(wr, k), frac);
+                }
+            }
+        }
     }
 }
 
@@ -255,9 +359,17 @@ template <bool HASQ>
 __device__ __forceinline__ void noise_update(const ModelArgs& a, double* tab, int mate, unsigned long long i, double frac) {
     const unsigned long long o = a.roff[mate][i];
     const int len = (int)(a.roff[mate][i + 1] - o);
-    const unsigned char* rb = a.rbase[mate] + o;
-    const unsigned char* rq = HASQ ? a.rqual[mate] + o : nullptr;
-    for (int k = 0; k < len; ++k) red_add(tab + (HASQ ? rq[k] * 5 + rb[k] : rb[k]), frac);
+    if (len <= 0) return;
+    FwdBytes rb(a.rbase[mate] + o);
+    FwdBytes rq(HASQ ? a.rqual[mate] + o : a.rbase[mate] + o, HASQ);
+    for (int k0 = 0; k0 < len; k0 += 8) {
+        const bool more = k0 + 8 < len;
+        const unsigned long long wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
+        const int n = min(8, len - k0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < n) red_add(tab + (HASQ ? byte_of(wq, k) * 5 + byte_of(wr, k) : byte_of(wr, k)), frac);
+    }
 }
 
 // RSPD::update, RSPD.h:43-59
@@ -319,6 +431,239 @@ __global__ void __launch_bounds__(kBlock) update_kernel(const ModelArgs a) {
     }
 }
 
+// ---- K3 for the quality models (SingleQModel / PairedEndQModel) -----------------------------------
+// The QProfile / NoiseQProfile statistics are 2500 + 500 cells of which ~20 ((frequent quality) x (matching base
+// pair)) receive almost every update: one red.global per base and hit (update_kernel above) serialises in L2 -
+// 1.8e9 reductions took 33 ms for 1 M paired reads.  Here every WARP owns a private copy of the two tables in
+// shared memory and no atomics are needed:
+//   * G lanes share a read (its bases and qualities are the same for all of them), each lane walks the transcript of
+//     one hit; at a base position the lanes' cells differ only where the transcripts differ, so normally the whole
+//     group agrees on the cell and ONE lane adds the group's summed weight;
+//   * the 32 / G groups of the warp take turns (their cells often coincide), ordered by __syncwarp;
+//   * positions where a group disagrees (isoform / allele differences) fall back to one lane at a time.
+// At the end the CTA adds its warps' tables and sends one reduction per non-zero cell to a replica of the global block.
+constexpr int kQMaxWarps = 16;   // warps per CTA; each owns (max quality + 1) * 30 doubles of shared memory
+
+struct RefStream {  // bases of a transcript in read direction: forward strand as stored, reverse strand complemented
+    const unsigned long long* q;
+    const unsigned long long* floor;
+    unsigned long long lo, hi;
+    unsigned sh;
+    bool rev;
+    __device__ __forceinline__ RefStream(const unsigned char* s, bool rev_, const unsigned char* base, bool active) {
+        const unsigned long long a = reinterpret_cast<unsigned long long>(s) - (rev_ ? 7ull : 0ull);
+        q = reinterpret_cast<const unsigned long long*>(a & ~7ull);
+        floor = reinterpret_cast<const unsigned long long*>(base);
+        sh = (unsigned)(a & 7ull) * 8u;
+        rev = rev_;
+        lo = hi = 0ull;
+        if (active) {
+            lo = q >= floor ? __ldg(q) : 0ull;
+            hi = __ldg(q + 1);
+        }
+    }
+    __device__ __forceinline__ unsigned long long next(bool fetch) {
+        const unsigned long long v = sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+        if (rev) {
+            --q;
+            hi = lo;
+            if (fetch) lo = q >= floor ? __ldg(q) : 0ull;
+        } else {
+            ++q;
+            lo = hi;
+            if (fetch) hi = __ldg(q + 1);
+        }
+        return v;
+    }
+    __device__ __forceinline__ int base_at(unsigned long long v, int k) const {
+        if (!rev) return (int)byte_of(v, k);
+        const int c = (int)byte_of(v, 7 - k);
+        return c < 4 ? 3 - c : 4;
+    }
+};
+
+template <int G>
+__device__ __forceinline__ double lane_group_sum(double v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int G, bool PAIRED>
+__global__ void __launch_bounds__(kQMaxWarps * 32, 1) update_q_kernel(const ModelArgs a) {
+    extern __shared__ double q_tabs[];
+    const int kQWarps = blockDim.x >> 5;
+    const int n_prof = a.q_rows * 25, kQTab = a.q_rows * 30;
+    constexpr int R = 32 / G;
+    constexpr int NM = PAIRED ? 2 : 1;   // mates
+    constexpr int NI = 2 * NM;           // (position, mate) items a group's doer lane handles per turn
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane % G, grp = lane / G;
+    double* tprof = q_tabs + warp * kQTab;
+    double* tnoise = tprof + n_prof;
+    for (int k = lane; k < kQTab; k += 32) tprof[k] = 0.0;
+    __syncwarp();
+    const unsigned group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    double* blk = a.stats + (size_t)((blockIdx.x * kQWarps + warp) % kReplicas) * a.stats_block;
+    double* t_gld = blk + a.o_gld;
+    double* t_rspd = blk + a.o_rspd;
+    const DevModel& m = a.m;
+
+    const unsigned long long warps_total = (unsigned long long)gridDim.x * kQWarps;
+    for (unsigned long long base = ((unsigned long long)blockIdx.x * kQWarps + warp) * R; base < a.N; base += warps_total * R) {
+        const unsigned long long i = base + grp;
+        const bool valid = i < a.N && !a.lowq[i];
+        unsigned long long fr = 0, to = 0;
+        double f0 = 0.0;
+        if (valid) {
+            fr = a.row_ptr[i];
+            to = a.row_ptr[i + 1];
+            f0 = a.post0[i];
+            if (f0 < kEpsilon) f0 = 0.0;  // updateNoise only if frac >= EPSILON
+        }
+        int len[NM];
+        unsigned long long ro[NM];
+#pragma unroll
+        for (int mt = 0; mt < NM; ++mt) {
+            ro[mt] = valid ? a.roff[mt][i] : 0ull;
+            len[mt] = valid ? (int)(a.roff[mt][i + 1] - ro[mt]) : 0;
+        }
+        // a read without hits still updates the noise statistics: at least one pass
+        const int n_pass = __reduce_max_sync(0xffffffffu, valid ? max(1, (int)((to - fr + G - 1) / G)) : 0);
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const unsigned long long j = fr + (unsigned long long)pass * G + g;
+            bool act = valid && j < to;
+            double frac = act ? a.post[j] : 0.0;
+            if (frac < kEpsilon) { act = false; frac = 0.0; }
+            int t = 0, dir = 0, p = 0, il = 0, fullLen = 1, totLen = 0;
+            if (act) {
+                const int sgn = a.sid[j];
+                t = abs(sgn);
+                dir = sgn < 0;
+                p = a.pos[j];
+                fullLen = a.full_len[t];
+                totLen = a.tot_len[t];
+                if (!PAIRED) {
+                    if (m.est_rspd) {  // one strand only (SingleQModel.h:180-184; helper models have mld == NULL)
+                        if (m.ori[0] >= 0.1 && dir == 0) rspd_update(a, t_rspd, p, fullLen, frac);
+                        if (m.ori[0] < 0.1 && dir == 1) rspd_update(a, t_rspd, totLen - p - len[0], fullLen, frac);
+                    }
+                } else {
+                    il = a.insertL[j];
+                    if (il > a.gld_lb && il <= a.gld_lb + a.gld_span) red_add(t_gld + (il - a.gld_lb), frac);
+                    if (m.est_rspd) rspd_update(a, t_rspd, dir == 0 ? p : totLen - p - il, fullLen, frac);
+                }
+            }
+            const bool noise_on = pass == 0 && valid && f0 != 0.0;  // the read's noise update rides on its first pass
+
+            bool on[NM], has[NM];
+            int leader[NM];
+            double wg[NM];
+            int lmax = 0;
+#pragma unroll
+            for (int mt = 0; mt < NM; ++mt) {
+                const int mpos = mt == 0 ? p : totLen - p - il;
+                on[mt] = act && len[mt] > 0 && mpos >= 0 && mpos + len[mt] <= totLen;  // QProfile::update guard
+                const unsigned bm = __ballot_sync(0xffffffffu, on[mt]) & group_mask;
+                has[mt] = bm != 0;
+                leader[mt] = bm ? __ffs(bm) - 1 : lane;
+                wg[mt] = lane_group_sum<G>(on[mt] ? frac : 0.0);
+                lmax = max(lmax, (on[mt] || noise_on) ? len[mt] : 0);
+            }
+            lmax = __reduce_max_sync(0xffffffffu, lmax);
+            const int mpos1 = PAIRED ? totLen - p - il : 0;
+            RefStream ref0(a.seq + (on[0] ? a.seq_off[t] + (dir == 0 ? p : totLen - 1 - p) : 0), dir != 0, a.seq, on[0]);
+            RefStream ref1(a.seq + (on[NM - 1] && PAIRED ? a.seq_off[t] + (dir != 0 ? mpos1 : totLen - 1 - mpos1) : 0),
+                           dir == 0, a.seq, PAIRED && on[NM - 1]);
+            const bool rd0 = valid && (has[0] || noise_on) && len[0] > 0;
+            const bool rd1 = PAIRED && valid && (has[NM - 1] || noise_on) && len[NM - 1] > 0;
+            FwdBytes rb0(a.rbase[0] + ro[0], rd0), rq0(a.rqual[0] + ro[0], rd0);
+            FwdBytes rb1(a.rbase[NM - 1] + ro[NM - 1], rd1), rq1(a.rqual[NM - 1] + ro[NM - 1], rd1);
+
+            for (int k0 = 0; k0 < lmax; k0 += 8) {
+                unsigned long long ws[NM], wr[NM], wq[NM];
+                ws[0] = ref0.next(on[0] && k0 + 8 < len[0]);
+                wr[0] = rb0.next(rd0 && k0 + 8 < len[0]);
+                wq[0] = rq0.next(rd0 && k0 + 8 < len[0]);
+                if (PAIRED) {
+                    ws[NM - 1] = ref1.next(on[NM - 1] && k0 + 8 < len[NM - 1]);
+                    wr[NM - 1] = rb1.next(rd1 && k0 + 8 < len[NM - 1]);
+                    wq[NM - 1] = rq1.next(rd1 && k0 + 8 < len[NM - 1]);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                    if (k0 + k >= lmax) break;  // warp-uniform
+                    // items x = 2 * mate + (position parity)
+                    int c[NI], c_lead[NI], qv[NI], rv[NI];
+                    bool inb[NI];
+#pragma unroll
+                    for (int x = 0; x < NI; ++x) {
+                        const int mt = x >> 1, kk = k + (x & 1);
+                        inb[x] = k0 + kk < len[mt];
+                        c[x] = mt == 0 ? ref0.base_at(ws[0], kk) : ref1.base_at(ws[NM - 1], kk);
+                        qv[x] = (int)byte_of(wq[mt], kk);
+                        rv[x] = (int)byte_of(wr[mt], kk);
+                        c_lead[x] = __shfl_sync(0xffffffffu, c[x], leader[mt]);
+                    }
+                    // Items on which a group agrees are added to the warp's shared-memory tables with its summed
+                    // weight; the 2 NI (profile, noise) items of a group are spread over its lanes so that the whole
+                    // warp issues ONE shared-memory atomic (a compare-and-swap loop in SASS; lanes of different groups
+                    // often name the same hot cell).  Where the transcripts of a group disagree (exon junctions,
+                    // alleles, spurious alignments) every lane sends its own weight to the global block instead -
+                    // those are the cold cells, so the L2 reductions do not pile up on one address.
+                    bool agree[NI];
+#pragma unroll
+                    for (int x = 0; x < NI; ++x) {
+                        const int mt = x >> 1;
+                        const unsigned dis = __ballot_sync(0xffffffffu, on[mt] && inb[x] && c[x] != c_lead[x]) & group_mask;
+                        agree[x] = dis == 0;
+                        if (!agree[x] && on[mt] && inb[x]) red_add(blk + (qv[x] * 5 + c[x]) * 5 + rv[x], frac);
+                    }
+#pragma unroll
+                    for (int x0 = 0; x0 < 2 * NI; x0 += G) {
+                        const int it = x0 + g;  // this lane's item: 0 .. NI-1 profile, NI .. 2 NI - 1 noise
+                        double* tab = tprof;
+                        int cell = 0;
+                        double w = 0.0;
+                        bool ok = false;
+#pragma unroll
+                        for (int x = 0; x < NI; ++x) {
+                            const int mt = x >> 1;
+                            if (it == x) {
+                                ok = has[mt] && inb[x] && agree[x];
+                                cell = (qv[x] * 5 + c_lead[x]) * 5 + rv[x];
+                                w = wg[mt];
+                            }
+                            if (it == NI + x) {
+                                ok = noise_on && inb[x];
+                                cell = qv[x] * 5 + rv[x];
+                                w = f0;
+                                tab = tnoise;
+                            }
+                        }
+                        if (ok) atomicAdd(tab + cell, w);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    double* out = a.stats + (size_t)(blockIdx.x % kReplicas) * a.stats_block;
+    for (int cidx = threadIdx.x; cidx < kQTab; cidx += blockDim.x) {
+        double v = 0.0;
+        for (int w = 0; w < kQWarps; ++w) v += q_tabs[w * kQTab + cidx];
+        if (v != 0.0) red_add(out + (cidx < n_prof ? (size_t)cidx : a.o_noise + (size_t)(cidx - n_prof)), v);
+    }
+}
+
+__global__ void max_u8_kernel(const unsigned char* v, unsigned long long n, unsigned int* out) {
+    unsigned int m = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        m = max(m, (unsigned int)v[i]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 __global__ void fold_replicas_kernel(double* stats, size_t block) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= block) return;
@@ -356,6 +701,7 @@ void fill_args(rsem_b200_ctx* c, ModelArgs& a) {
     int rows = hasq ? 100 : std::min(c->model.pro_len, std::max(c->reads.max_len, 1));
     if ((size_t)rows * 200 + 4096 > 200 * 1024) rows = 0;
     a.prof_rows_smem = rows;
+    a.q_rows = c->reads.qmax >= 0 ? std::min(c->reads.qmax + 1, 100) : 100;
     a.stats = c->stats_buf;
     a.stats_block = c->stats.total_doubles;
     a.o_noise = c->stats.noise_profile ? (size_t)(c->stats.noise_profile - c->stats_buf) : 0;
@@ -384,9 +730,24 @@ int launch_conprb_g(rsem_b200_ctx* c, const ModelArgs& a, unsigned grid, size_t 
     return 0;
 }
 
+template <int G, bool PAIRED>
+int launch_update_q(rsem_b200_ctx* c, const ModelArgs& a) {
+    auto k = update_q_kernel<G, PAIRED>;
+    const size_t per_warp = (size_t)a.q_rows * 30 * sizeof(double);
+    const int warps = (int)std::max<size_t>(1, std::min<size_t>(kQMaxWarps, (size_t)(200 * 1024) / per_warp));
+    const size_t smem = per_warp * warps;
+    RB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<c->sm_count, warps * 32, smem, c->stream>>>(a);
+    RB_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
 template <int G>
 int launch_update_g(rsem_b200_ctx* c, const ModelArgs& a, unsigned grid) {
     const bool hasq = c->model.model_type & 1, paired = c->model.model_type >= 2;
+    static const bool global_reds = getenv("RSEM_B200_K3") && !strcmp(getenv("RSEM_B200_K3"), "global");
+    if (hasq && !global_reds) return paired ? launch_update_q<G, true>(c, a) : launch_update_q<G, false>(c, a);
     if (hasq && paired) update_kernel<G, true, true><<<grid, kBlock, 0, c->stream>>>(a);
     else if (hasq) update_kernel<G, true, false><<<grid, kBlock, 0, c->stream>>>(a);
     else if (paired) update_kernel<G, false, true><<<grid, kBlock, 0, c->stream>>>(a);
@@ -440,6 +801,21 @@ int model_launch_update(rsem_b200_ctx* c) {
     c->stats.rspd_pdf = c->stats_buf + n_prof + n_noise + n_gld;
     RB_CUDA(cudaMemsetAsync(c->stats_buf, 0, block * kReplicas * sizeof(double), c->stream));
     if (c->N == 0) return 0;
+    if (hasq && c->reads.qmax < 0) {  // largest quality value of the resident read set, once per upload
+        unsigned int* d_max = nullptr;
+        unsigned int h_max = 0;
+        RB_CUDA(cudaMalloc(&d_max, sizeof(unsigned int)));
+        RB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned int), c->stream));
+        for (int mt = 0; mt < c->reads.n_mates; ++mt) {
+            const unsigned long long nb = c->reads.total_bases[mt];
+            if (nb) max_u8_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->reads.qual[mt], nb, d_max);
+        }
+        RB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+        RB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(d_max);
+        c->reads.qmax = (int)h_max;
+        c->launches += c->reads.n_mates;
+    }
     ModelArgs a;
     fill_args(c, a);
     const int G = c->group;

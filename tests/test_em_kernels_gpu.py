@@ -114,3 +114,106 @@ def test_all_rows_below_epsilon(ctx):
     stats, _ = ctx.em_rounds(1, 1, 20, 100, 3.0)
     assert stats[0][0] == 3.0
     assert np.array_equal(ctx.get_theta(), np.array([1.0, 0.0, 0.0]))
+
+
+def test_rows_longer_than_a_stage_use_the_unstaged_kernel(ctx, oracle):
+    """a 6000-hit row does not fit a shared-memory stage: auto must fall back to the direct kernel and stay exact"""
+    rng = np.random.default_rng(3)
+    row_ptr, sid, conprb, ncpv = synth.random_matrix(3000, 8000, 7, seed=21)
+    # splice one very long row into the middle
+    long_deg = 6000
+    mid = 1500
+    h = int(row_ptr[mid])
+    long_sid = (rng.permutation(8000)[:long_deg] + 1).astype(np.int32)
+    long_con = 10.0 ** rng.uniform(-60, -3, size=long_deg)
+    sid = np.concatenate([sid[:h], long_sid, sid[h:]])
+    conprb = np.concatenate([conprb[:h], long_con, conprb[h:]])
+    row_ptr = np.concatenate([row_ptr[:mid + 1], row_ptr[mid:] + np.uint64(long_deg)]).astype(np.uint64)
+    ncpv = np.concatenate([ncpv[:mid], [1e-50], ncpv[mid:]])
+    N, M = len(ncpv), 8000
+    assert row_ptr[-1] == len(sid) and len(row_ptr) == N + 1
+    n0 = 50.0
+    theta0 = synth.init_theta(M, n0, N + n0)
+    ctx.set_estep_variant(0)
+    ctx.upload_hits(row_ptr, sid, M)
+    ctx.upload_conprb(conprb, ncpv)
+    ctx.set_theta(theta0)
+    ctx.em_rounds(1, 5, 20, 10000, n0)
+    theta_ref, _, _ = oracle.em_rounds(row_ptr, sid, conprb, ncpv, theta0, n0, 1, 5, 20, 10000)
+    _check_theta(ctx.get_theta(), theta_ref)
+
+
+@pytest.mark.parametrize("threads", [128, 256, 512, 1024])
+def test_row_group_kernel_tile_geometries(ctx, oracle, threads, monkeypatch):
+    """the row-group kernel on every CTA / tile geometry it is instantiated for"""
+    monkeypatch.setenv("RSEM_B200_CTA_THREADS", str(threads))
+    row_ptr, sid, conprb, ncpv = synth.random_matrix(60000, 9000, 21, seed=threads)
+    n0 = 3000.0
+    theta0 = synth.init_theta(9000, n0, 60000 + n0)
+    ctx.set_estep_variant(4)
+    ctx.upload_hits(row_ptr, sid, 9000)
+    ctx.upload_conprb(conprb, ncpv)
+    ctx.set_theta(theta0)
+    ctx.em_rounds(1, 6, 20, 10000, n0)
+    theta_ref, _, _ = oracle.em_rounds(row_ptr, sid, conprb, ncpv, theta0, n0, 1, 6, 20, 10000)
+    _check_theta(ctx.get_theta(), theta_ref)
+    counts = ctx.expected_weights()
+    post, post0 = ctx.download_conprb()
+    c_ref, p_ref, p0_ref = oracle.estep(row_ptr, sid, conprb, ncpv, ctx.get_theta(), want_post=True)
+    assert np.allclose(counts, c_ref, rtol=1e-10, atol=1e-13)
+    assert np.allclose(post, p_ref, rtol=1e-12, atol=0)
+    assert np.allclose(post0, p0_ref, rtol=1e-12, atol=0)
+    ctx.set_estep_variant(0)
+
+
+def test_full_size_properties(ctx):
+    """BASELINE configs[2] (C3: 50 M reads x 200 k transcripts, 1e9 hits) is far beyond what the CPU oracle finishes
+    in seconds, so the full size is checked through properties that do not depend on it:
+      * theta sums to 1 and the expected counts sum to the number of reads (every row has a positive sum);
+      * scaling every conprb / ncpv by 2^-20 (exact in fp64) leaves the posteriors, hence theta, unchanged;
+      * a prefix of the matrix goes through the small-size upload path that the oracle tests cover."""
+    torch = pytest.importorskip("torch")
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    import bench
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~45 GB of free device memory")
+    dev = torch.device("cuda:0")
+    N, M, deg = 50_000_000, 200_000, 20
+    row_ptr, sid, conprb, ncpv, H = bench.gen_matrix_torch(torch, dev, N, M, deg, seed=77)
+    n0 = N / 20
+    theta0 = synth.init_theta(M, n0, N + n0)
+    ctx.set_estep_variant(0)
+    ctx.adopt_device_matrix(N, H, M, row_ptr.data_ptr(), sid.data_ptr(), conprb.data_ptr(), ncpv.data_ptr())
+    ctx.set_theta(theta0)
+    stats, _ = ctx.em_rounds(1, 3, 20, 10000, n0)
+    th_a = ctx.get_theta()
+    assert abs(th_a.sum() - 1.0) < 1e-12
+    for s, _, _ in stats:
+        assert abs(s - (N + n0)) <= 1e-9 * (N + n0)  # sum of counts + N0: every read distributes exactly one unit
+    # exact power-of-two rescaling
+    conprb.mul_(2.0 ** -20)
+    ncpv.mul_(2.0 ** -20)
+    torch.cuda.synchronize()
+    ctx.adopt_device_matrix(N, H, M, row_ptr.data_ptr(), sid.data_ptr(), conprb.data_ptr(), ncpv.data_ptr())
+    ctx.set_theta(theta0)
+    ctx.em_rounds(1, 3, 20, 10000, n0)
+    th_b = ctx.get_theta()
+    big = th_a >= 1e-7
+    assert np.all(np.abs(th_a[big] - th_b[big]) <= 1e-11 * th_a[big])
+    # a prefix of the same matrix through the small-size (oracle-checked) upload path: one unit per read again
+    n_sub = 100_000
+    h_sub = int(row_ptr[n_sub].item())
+    rp = row_ptr[: n_sub + 1].cpu().numpy().astype(np.uint64)
+    sd = sid[:h_sub].cpu().numpy()
+    cp = conprb[:h_sub].cpu().numpy()
+    nc = ncpv[:n_sub].cpu().numpy()
+    ctx.upload_hits(rp, sd, M)  # releases the adopted pointers before the tensors go away
+    ctx.upload_conprb(cp, nc)
+    del row_ptr, sid, conprb, ncpv
+    torch.cuda.empty_cache()
+    ctx.set_theta(th_a)
+    counts_sub = ctx.expected_weights()
+    assert abs(counts_sub.sum() - n_sub) <= 1e-9 * n_sub
