@@ -50,7 +50,8 @@ def build_host(force: bool = False):
     shared = [s for s in common if s not in mains]
     deps = common + glob.glob(os.path.join(HOST, "*.hpp")) + [os.path.join(ROOT, "include", "rsem_b200.h")]
     for m in mains:
-        name = {"main_em.cpp": "rsem-run-em", "main_gibbs.cpp": "rsem-run-gibbs"}[os.path.basename(m)]
+        name = {"main_em.cpp": "rsem-run-em", "main_gibbs.cpp": "rsem-run-gibbs",
+                "main_selftest.cpp": "rsem-b200-host-selftest"}[os.path.basename(m)]
         out = os.path.join(ROOT, "bin", name)
         if force or _newer(out, deps + [os.path.join(ROOT, "rsem_b200", "librsem_b200.so")]):
             _run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", out, m, *shared,

@@ -1,0 +1,89 @@
+// rsem-b200-host-selftest: runs the multi-threaded host parsers / formatters of the drop-in executables without a
+// GPU and dumps what they produced as raw binary arrays, so that the CPU test suite can compare them with an
+// independent parse of the same text files and across thread counts.  Test tooling, not part of the product path.
+//
+//   rsem-b200-host-selftest <imdName> <read_type> <threads> <seedLen> <outPrefix>
+//
+// writes <outPrefix>.{row_ptr.u64,sid.i32,pos.i32,insertL.i32,off<m>.u64,base<m>.u8,qual<m>.u8,lowq.u8} and
+// <outPrefix>.ofg (write_ofg of a synthetic conprb) plus the arrays load_ofg reads back from it.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "host.hpp"
+
+using namespace host;
+
+template <class T>
+static void dump(const std::string& path, const std::vector<T>& v) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) die("cannot write " + path);
+    if (!v.empty() && fwrite(v.data(), sizeof(T), v.size(), f) != v.size()) die("short write " + path);
+    fclose(f);
+}
+
+int main(int argc, char** argv) {
+    if (argc != 6) {
+        fprintf(stderr, "Usage: rsem-b200-host-selftest imdName read_type threads seedLen outPrefix\n");
+        return -1;
+    }
+    const std::string imd = argv[1], out = argv[5];
+    const int read_type = atoi(argv[2]);
+    g_io_threads = atoi(argv[3]);
+    const int seed_len = atoi(argv[4]);
+    g_verbose = false;
+
+    unsigned long long n1 = 0;
+    {
+        FILE* f = fopen((imd + ".dat").c_str(), "r");
+        if (!f || fscanf(f, "%llu", &n1) != 1) die("cannot read " + imd + ".dat");
+        fclose(f);
+    }
+    HitStore h;
+    load_dat(imd + ".dat", read_type, n1, h);
+    dump(out + ".row_ptr.u64", h.row_ptr);
+    dump(out + ".sid.i32", h.sid);
+    dump(out + ".pos.i32", h.pos);
+    dump(out + ".insertL.i32", h.insertL);
+
+    ReadStore rs;
+    std::vector<std::string> short_names;
+    uint64_t n_short = 0;
+    parse_reads(imd, 1, read_type, false, seed_len, rs, &short_names, &n_short);
+    for (int m = 0; m < rs.n_mates; ++m) {
+        dump(out + ".off" + std::to_string(m) + ".u64", rs.off[m]);
+        dump(out + ".base" + std::to_string(m) + ".u8", rs.base[m]);
+        dump(out + ".qual" + std::to_string(m) + ".u8", rs.qual[m]);
+    }
+    dump(out + ".lowq.u8", rs.lowq);
+
+    // .ofg round trip on a synthetic matrix derived from the hit indices (includes dropped entries and rows)
+    std::vector<double> conprb(h.H), ncpv(h.N);
+    for (uint64_t j = 0; j < h.H; ++j) {
+        const uint64_t x = j * 2654435761ull % 1000003ull;
+        conprb[j] = x % 17 == 0 ? 0.0 : std::pow(10.0, -3.0 - (double)(x % 290)) * (1.0 + (double)(x % 97) / 97.0);
+    }
+    for (uint64_t i = 0; i < h.N; ++i) {
+        const uint64_t x = i * 40503ull % 65521ull;
+        ncpv[i] = x % 5 == 0 ? 0.0 : std::pow(10.0, -40.0 - (double)(x % 200));
+    }
+    int M = 0;
+    for (int32_t s : h.sid) M = std::max(M, std::abs(s));
+    write_ofg(out + ".ofg", M, 12345, h, conprb, ncpv);
+    uint64_t n0 = 0;
+    std::vector<uint64_t> rp;
+    std::vector<int32_t> sid;
+    std::vector<double> con;
+    load_ofg(out + ".ofg", M, n0, rp, sid, con);
+    dump(out + ".ofg_row_ptr.u64", rp);
+    dump(out + ".ofg_sid.i32", sid);
+    dump(out + ".ofg_con.f64", con);
+    dump(out + ".in_con.f64", conprb);
+    dump(out + ".in_ncpv.f64", ncpv);
+    printf("N %llu H %llu reads %llu short %llu N0 %llu ofg_rows %zu ofg_entries %zu\n", (unsigned long long)h.N,
+           (unsigned long long)h.H, (unsigned long long)rs.n, (unsigned long long)n_short, (unsigned long long)n0,
+           rp.empty() ? (size_t)0 : rp.size() - 1, sid.size());
+    return 0;
+}
