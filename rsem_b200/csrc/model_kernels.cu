@@ -135,6 +135,45 @@ struct RevBytes {  // bytes p[0], p[-1], p[-2], ... 8 at a time; never loads bel
 };
 __device__ __forceinline__ unsigned byte_of(unsigned long long w, int k) { return (unsigned)(w >> (8 * k)) & 0xffu; }
 
+struct RefStream {  // bases of a transcript in read direction: forward strand as stored, reverse strand complemented
+    const unsigned long long* q;
+    const unsigned long long* floor;
+    unsigned long long lo, hi;
+    unsigned sh;
+    bool rev;
+    __device__ __forceinline__ RefStream(const unsigned char* s, bool rev_, const unsigned char* base, bool active) {
+        const unsigned long long a = reinterpret_cast<unsigned long long>(s) - (rev_ ? 7ull : 0ull);
+        q = reinterpret_cast<const unsigned long long*>(a & ~7ull);
+        floor = reinterpret_cast<const unsigned long long*>(base);
+        sh = (unsigned)(a & 7ull) * 8u;
+        rev = rev_;
+        lo = hi = 0ull;
+        if (active) {
+            lo = q >= floor ? __ldg(q) : 0ull;
+            hi = __ldg(q + 1);
+        }
+    }
+    __device__ __forceinline__ unsigned long long next(bool fetch) {
+        const unsigned long long v = sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+        if (rev) {
+            --q;
+            hi = lo;
+            if (fetch) lo = q >= floor ? __ldg(q) : 0ull;
+        } else {
+            ++q;
+            lo = hi;
+            if (fetch) hi = __ldg(q + 1);
+        }
+        return v;
+    }
+    __device__ __forceinline__ int base_at(unsigned long long v, int k) const {
+        if (!rev) return (int)byte_of(v, k);
+        const int c = (int)byte_of(v, 7 - k);
+        return c < 4 ? 3 - c : 4;
+    }
+};
+
+
 // product over the bases of one mate of p[row][ref][read]; row = quality (Q models) or position.
 // Multiplication order = base order, as in the reference.
 template <bool HASQ>
@@ -150,35 +189,18 @@ __device__ __forceinline__ double seq_prob(const ModelArgs& a, const double* pro
     if (len <= 0) return 1.0;
     FwdBytes rb(a.rbase[mate] + o);
     FwdBytes rq(HASQ ? a.rqual[mate] + o : a.rbase[mate] + o, HASQ);
-    const unsigned char* s = a.seq + a.seq_off[sid] + (dir == 0 ? pos : totLen - 1 - pos);
+    // one loop for both strands (the lanes of a warp hold hits of either orientation; two loops would both be executed)
+    RefStream sb(a.seq + a.seq_off[sid] + (dir == 0 ? pos : totLen - 1 - pos), dir != 0, a.seq, true);
     double prob = 1.0;
-    if (dir == 0) {
-        FwdBytes sb(s);
-        for (int k0 = 0; k0 < len; k0 += 8) {
-            const bool more = k0 + 8 < len;
-            const unsigned long long ws = sb.next(more), wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
-            const int n = min(8, len - k0);
+    for (int k0 = 0; k0 < len; k0 += 8) {
+        const bool more = k0 + 8 < len;
+        const unsigned long long ws = sb.next(more), wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
+        const int n = min(8, len - k0);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (k < n) {
-                    const int row = HASQ ? (int)byte_of(wq, k) : k0 + k;
-                    prob *= prof[(row * 5 + (int)byte_of(ws, k)) * 5 + (int)byte_of(wr, k)];
-                }
-            }
-        }
-    } else {
-        RevBytes sb(s, a.seq);
-        for (int k0 = 0; k0 < len; k0 += 8) {
-            const bool more = k0 + 8 < len;
-            const unsigned long long ws = sb.next(more), wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
-            const int n = min(8, len - k0);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (k < n) {
-                    const int c = (int)byte_of(ws, 7 - k);
-                    const int row = HASQ ? (int)byte_of(wq, k) : k0 + k;
-                    prob *= prof[(row * 5 + (c < 4 ? 3 - c : 4)) * 5 + (int)byte_of(wr, k)];
-                }
+        for (int k = 0; k < 8; ++k) {
+            if (k < n) {
+                const int row = HASQ ? (int)byte_of(wq, k) : k0 + k;
+                prob *= prof[(row * 5 + sb.base_at(ws, k)) * 5 + (int)byte_of(wr, k)];
             }
         }
     }
@@ -270,28 +292,24 @@ __device__ double noise_conprb(const ModelArgs& a, const double* nprof, unsigned
     return w < kEpsilon ? 0.0 : prob / w;
 }
 
-// stage the first `rows` rows (25 doubles each) of the profile + the noise table in shared memory
-__device__ __forceinline__ void stage_tables(const ModelArgs& a, double* smem, const double*& prof, const double*& nprof,
-                                             bool hasq) {
-    prof = a.m.profile;
-    nprof = a.m.noise_profile;
-    if (a.prof_rows_smem > 0) {
-        const int n = a.prof_rows_smem * 25;
-        for (int k = threadIdx.x; k < n; k += blockDim.x) smem[k] = a.m.profile[k];
-        const int nn = hasq ? 500 : 5;
-        for (int k = threadIdx.x; k < nn; k += blockDim.x) smem[n + k] = a.m.noise_profile[k];
-        __syncthreads();
-        prof = smem;
-        nprof = smem + n;
-    }
-}
-
 // ---- K1 ---------------------------------------------------------------------------------------
-template <int G, bool HASQ, bool PAIRED>
+// STAGED: the first prof_rows_smem rows (25 doubles each) of the profile + the noise table are copied to shared memory
+// and read from there.  It is a template parameter so that the table pointer is known to be a shared-memory address
+// (LDS instead of generic LD.E, which the per-base lookups are bound by).
+template <int G, bool HASQ, bool PAIRED, bool STAGED>
 __global__ void __launch_bounds__(kBlock) conprb_kernel(const ModelArgs a) {
     extern __shared__ double smem_tab[];
-    const double *prof, *nprof;
-    stage_tables(a, smem_tab, prof, nprof, HASQ);
+    const double* prof = a.m.profile;
+    const double* nprof = a.m.noise_profile;
+    if (STAGED) {
+        const int n = a.prof_rows_smem * 25;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) smem_tab[k] = a.m.profile[k];
+        const int nn = HASQ ? 500 : 5;
+        for (int k = threadIdx.x; k < nn; k += blockDim.x) smem_tab[n + k] = a.m.noise_profile[k];
+        __syncthreads();
+        prof = smem_tab;
+        nprof = smem_tab + n;
+    }
     const int lane = threadIdx.x & 31, g = lane % G;
     const unsigned long long groups_total = (unsigned long long)gridDim.x * (kBlock / G);
     for (unsigned long long i = (unsigned long long)blockIdx.x * (kBlock / G) + threadIdx.x / G; i < a.N; i += groups_total) {
@@ -443,44 +461,6 @@ __global__ void __launch_bounds__(kBlock) update_kernel(const ModelArgs a) {
 //   * positions where a group disagrees (isoform / allele differences) fall back to one lane at a time.
 // At the end the CTA adds its warps' tables and sends one reduction per non-zero cell to a replica of the global block.
 constexpr int kQMaxWarps = 16;   // warps per CTA; each owns (max quality + 1) * 30 doubles of shared memory
-
-struct RefStream {  // bases of a transcript in read direction: forward strand as stored, reverse strand complemented
-    const unsigned long long* q;
-    const unsigned long long* floor;
-    unsigned long long lo, hi;
-    unsigned sh;
-    bool rev;
-    __device__ __forceinline__ RefStream(const unsigned char* s, bool rev_, const unsigned char* base, bool active) {
-        const unsigned long long a = reinterpret_cast<unsigned long long>(s) - (rev_ ? 7ull : 0ull);
-        q = reinterpret_cast<const unsigned long long*>(a & ~7ull);
-        floor = reinterpret_cast<const unsigned long long*>(base);
-        sh = (unsigned)(a & 7ull) * 8u;
-        rev = rev_;
-        lo = hi = 0ull;
-        if (active) {
-            lo = q >= floor ? __ldg(q) : 0ull;
-            hi = __ldg(q + 1);
-        }
-    }
-    __device__ __forceinline__ unsigned long long next(bool fetch) {
-        const unsigned long long v = sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
-        if (rev) {
-            --q;
-            hi = lo;
-            if (fetch) lo = q >= floor ? __ldg(q) : 0ull;
-        } else {
-            ++q;
-            lo = hi;
-            if (fetch) hi = __ldg(q + 1);
-        }
-        return v;
-    }
-    __device__ __forceinline__ int base_at(unsigned long long v, int k) const {
-        if (!rev) return (int)byte_of(v, k);
-        const int c = (int)byte_of(v, 7 - k);
-        return c < 4 ? 3 - c : 4;
-    }
-};
 
 template <int G>
 __device__ __forceinline__ double lane_group_sum(double v) {
@@ -716,9 +696,13 @@ int launch_conprb_g(rsem_b200_ctx* c, const ModelArgs& a, unsigned grid, size_t 
     const bool hasq = c->model.model_type & 1, paired = c->model.model_type >= 2;
 #define RB_LAUNCH(Q, P)                                                                                      \
     do {                                                                                                     \
-        auto k = conprb_kernel<G, Q, P>;                                                                     \
-        if (smem > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k<<<grid, kBlock, smem, c->stream>>>(a);                                                             \
+        if (smem) {                                                                                          \
+            auto k = conprb_kernel<G, Q, P, true>;                                                           \
+            if (smem > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k<<<grid, kBlock, smem, c->stream>>>(a);                                                         \
+        } else {                                                                                             \
+            conprb_kernel<G, Q, P, false><<<grid, kBlock, 0, c->stream>>>(a);                                \
+        }                                                                                                    \
     } while (0)
     if (hasq && paired) RB_LAUNCH(true, true);
     else if (hasq) RB_LAUNCH(true, false);
