@@ -64,6 +64,11 @@ def build_tools(force: bool = False):
     out = os.path.join(ROOT, "tools", "gen_dataset")
     if force or _newer(out, [src]):
         _run(["g++", "-O2", "-std=c++17", "-o", out, src])
+    # micro-benchmark behind the lane-mapping table in profiles/README.md (tools/gpu/red_bench.sh)
+    src = os.path.join(ROOT, "tools", "micro", "red_bench.cu")
+    out = os.path.join(ROOT, "tools", "micro", "red_bench")
+    if os.path.exists(src) and (force or _newer(out, [src])):
+        _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", out, src])
 
 
 def build_oracle():
