@@ -212,6 +212,8 @@ def run_ours(args):
     N, M, deg = WORKLOADS[name]
     if args.scale != 1.0:
         N = max(1000, int(N * args.scale))
+    if args.deg:
+        deg = args.deg
 
     row_ptr, sid, conprb, ncpv, H = gen_matrix_torch(torch, dev, N, M, deg, seed=1234 + rank)
     if args.sort_rows:
@@ -443,6 +445,7 @@ def main():
     ap.add_argument("--sort-rows", default="", choices=["", "start", "deg"],
                     help="experiment: reorder the reads by first transcript id or by degree")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel experiments)")
+    ap.add_argument("--deg", type=int, default=0, help="experiment: override the mean number of hits per read")
     ap.add_argument("--ref-reads", type=int, default=2_000_000, help="reads in the reference arm's bounded sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
