@@ -368,6 +368,7 @@ def run_ours(args):
                        "l2_policy": "inputs (12.8 GB) larger than L2, no flush needed" if H * 12 > 2e8 else "inputs fit L2",
                        "parallelism": f"reads sharded over {world} GPU(s), ncclAllReduce(count) per round" if world > 1 else "1 GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "class_layout": ctx.class_layout_info(),
         }
         print(json.dumps(out), flush=True)
     ctx.close()

@@ -173,7 +173,9 @@ int rsem_b200_em_model_round(rsem_b200_ctx* ctx, double n0, rsem_b200_model_stat
 
 /* Final pass with calcExpectedWeights = true (EM.cpp:460-478): E-step with the current theta that
  * overwrites hit.conprb / ncpv with the posteriors and returns the expected counts
- * (M + 1, summed over ranks, WITHOUT adding N0).  theta is not changed.                         */
+ * (M + 1, summed over ranks, WITHOUT adding N0).  theta is not changed.  Afterwards conprb / ncpv
+ * hold posteriors (read them with download_conprb): further E-steps on this context need a new
+ * upload_conprb / calc_conprb first and fail with RSEM_B200_ERR_ARG otherwise.                   */
 int rsem_b200_expected_weights(rsem_b200_ctx* ctx, double* counts_out);
 
 /* ---- Gibbs (rsem-run-gibbs, Gibbs.cpp:265-353) ------------------------------------------------
@@ -219,10 +221,17 @@ int rsem_b200_launch_count(rsem_b200_ctx* ctx, uint64_t* launches);
 int rsem_b200_estep_timing(rsem_b200_ctx* ctx, double* total_ms, uint64_t* launches, int32_t reset);
 /* enable per-launch event timing of K2 (off by default: it adds two event records per round)    */
 int rsem_b200_set_profiling(rsem_b200_ctx* ctx, int32_t enabled);
-/* select the E/M kernel variant: 0 = auto, 1 = CTA-staged tiles (TMA), 2 = direct (no smem staging),
- * 3 = warp-pipelined tiles (TMA, no CTA barriers), 4 = row groups on CTA-staged tiles (TMA, no CTA
- * barriers, dynamic row batches)                                                                 */
+/* select the E/M kernel variant: 0 = auto (equivalence-class layout for frozen-conprb rounds, row groups when
+ * posteriors are written), 1 = CTA-staged tiles (TMA), 2 = direct (no smem staging), 3 = warp-pipelined tiles
+ * (TMA, no CTA barriers), 4 = row groups on CTA-staged tiles (TMA, no CTA barriers, dynamic row batches),
+ * 5 = equivalence-class layout, fail if the matrix is outside its limits                           */
 int rsem_b200_set_estep_variant(rsem_b200_ctx* ctx, int32_t variant);
+
+/* Equivalence-class layout the frozen-conprb rounds run on (derived from the hit matrix on first use; reads with
+ * identical transcript lists - the reference has no counterpart, it walks HitContainer row by row, EM.cpp:199-244).
+ * out[8] = { built (0/1), rows in the layout, rows handled by the long-row launch, segments, batches, tiles,
+ *            staged doubles (conprb + ncpv), staged ids }.  Streamed bytes per round = 8 out[6] + 4 out[7] + 16 out[4]. */
+int rsem_b200_class_layout_info(rsem_b200_ctx* ctx, uint64_t* out /* 8 */);
 
 #ifdef __cplusplus
 }

@@ -76,7 +76,7 @@ SYMBOLS = [
     "rsem_b200_set_model", "rsem_b200_calc_conprb", "rsem_b200_set_theta", "rsem_b200_get_theta",
     "rsem_b200_em_rounds", "rsem_b200_em_model_round", "rsem_b200_expected_weights", "rsem_b200_gibbs_upload",
     "rsem_b200_gibbs_run", "rsem_b200_launch_count", "rsem_b200_estep_timing", "rsem_b200_set_profiling",
-    "rsem_b200_set_estep_variant",
+    "rsem_b200_set_estep_variant", "rsem_b200_class_layout_info",
 ]
 
 
@@ -272,6 +272,14 @@ class Context:
 
     def set_profiling(self, on: bool):
         self.lib.check(self.lib.dll.rsem_b200_set_profiling(self._h, C.c_int32(int(on))))
+
+    def class_layout_info(self) -> dict:
+        out = (C.c_uint64 * 8)()
+        self.lib.check(self.lib.dll.rsem_b200_class_layout_info(self._h, out))
+        keys = ("built", "rows", "long_rows", "segments", "batches", "tiles", "vals", "ids")
+        d = dict(zip(keys, (int(x) for x in out)))
+        d["bytes_per_round"] = 8 * d["vals"] + 4 * d["ids"] + 16 * d["batches"]
+        return d
 
     def set_estep_variant(self, v: int):
         self.lib.check(self.lib.dll.rsem_b200_set_estep_variant(self._h, C.c_int32(v)))

@@ -47,8 +47,10 @@ void free_hits(rsem_b200_ctx* c) {
     if (c->wtile_row) { cudaFree(c->wtile_row); c->wtile_row = nullptr; }
     if (c->wtile_hit) { cudaFree(c->wtile_hit); c->wtile_hit = nullptr; }
     c->n_tiles = c->n_wtiles = 0;
+    class_free(c);
     c->N = c->H = 0;
     c->conprb_valid = false;
+    c->conprb_epoch++;
 }
 
 void free_reads(rsem_b200_ctx* c) {
@@ -286,6 +288,7 @@ int rsem_b200_upload_conprb(rsem_b200_ctx* c, const double* conprb, const double
     RB_CUDA(cudaMemcpyAsync(c->ncpv, ncpv, c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));
     c->conprb_valid = true;
+    c->conprb_epoch++;
     return 0;
 }
 
@@ -318,6 +321,7 @@ int rsem_b200_adopt_device_matrix(rsem_b200_ctx* c, uint64_t N, uint64_t H, int3
     if (int rc = finish_matrix_setup(c)) return rc;
     RB_CUDA(cudaStreamSynchronize(c->stream));
     c->conprb_valid = true;
+    c->conprb_epoch++;
     return 0;
 }
 
@@ -440,6 +444,7 @@ int rsem_b200_calc_conprb(rsem_b200_ctx* c) {
     if (int rc = model_launch_conprb(c)) return rc;
     if (int rc = check_err_flag(c)) return rc;
     c->conprb_valid = true;
+    c->conprb_epoch++;
     return 0;
 }
 
@@ -548,6 +553,9 @@ int rsem_b200_expected_weights(rsem_b200_ctx* c, double* counts_out) {
     RB_CUDA(cudaMemsetAsync(c->count, 0, ((size_t)c->M + 1) * sizeof(double), c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));
     harvest_events(c);
+    // conprb / ncpv now hold posteriors, not conditional probabilities: another E-step on them would be wrong
+    c->conprb_valid = false;
+    c->conprb_epoch++;
     return 0;
 }
 
@@ -600,8 +608,22 @@ int rsem_b200_set_profiling(rsem_b200_ctx* c, int32_t enabled) {
     return 0;
 }
 
+int rsem_b200_class_layout_info(rsem_b200_ctx* c, uint64_t* out) {
+    RB_ARG(c && out, "NULL argument");
+    const ClassLayout& L = c->cls;
+    out[0] = L.built ? 1 : 0;
+    out[1] = L.n_rows;
+    out[2] = L.n_long;
+    out[3] = L.n_segs;
+    out[4] = L.n_batches;
+    out[5] = L.n_tiles;
+    out[6] = L.n_vals;
+    out[7] = L.n_ids;
+    return 0;
+}
+
 int rsem_b200_set_estep_variant(rsem_b200_ctx* c, int32_t v) {
-    RB_ARG(c && v >= 0 && v <= 4, "variant must be 0..4");
+    RB_ARG(c && v >= 0 && v <= 5, "variant must be 0..5");
     c->variant = v;
     return 0;
 }

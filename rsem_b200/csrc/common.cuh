@@ -107,6 +107,23 @@ struct DevGibbs {
     uint32_t max_len = 0;
 };
 
+// equivalence-class layout of the hit matrix for the frozen-conprb rounds (class_kernels.cu)
+struct ClassLayout {
+    bool built = false;
+    uint64_t vals_epoch = 0;        // conprb epoch the value stream was gathered at (0 = never)
+    uint32_t n_rows = 0, n_long = 0, n_segs = 0, n_batches = 0, n_tiles = 0, R = 0;
+    int threads = 512;              // CTA size of the class kernel
+    uint64_t n_vals = 0, n_ids = 0;
+    double* vals = nullptr;         // per batch: ncpv [row][segment], then conprb [(row, column)][segment]
+    int32_t* ids = nullptr;         // per batch: transcript ids [column][segment] (or [column] for a one-class batch)
+    void* desc = nullptr;           // BatchDesc[n_batches]
+    void* tile = nullptr;           // TileRec[n_tiles + 1]
+    uint32_t* batch_first = nullptr;  // first segment (final order) of every batch
+    uint32_t* fseg_first = nullptr;   // first sorted row position of every segment (final order)
+    uint32_t* rows = nullptr;         // sorted position -> original row
+    uint32_t* long_rows = nullptr;    // original rows with more than kLongDeg hits
+};
+
 }  // namespace rsem_b200
 
 struct rsem_b200_ctx {
@@ -131,6 +148,8 @@ struct rsem_b200_ctx {
     double* post = nullptr;   // posterior / frac per hit (lazily allocated)
     double* post0 = nullptr;  // posterior of the noise entry per read
     bool conprb_valid = false;
+    uint64_t conprb_epoch = 1;  // bumped whenever conprb / ncpv change (derived layouts compare it)
+    rsem_b200::ClassLayout cls;
 
     // E-step tiling (em_kernels.cu)
     uint64_t* tile_row = nullptr;
@@ -145,7 +164,7 @@ struct rsem_b200_ctx {
     int rows_group = 8;   // lanes per row of the row-group K2 (variant 4)
     bool tiles_for_rows = true;  // tiles built for the row-group kernel (no row-start masks) or for the three-phase one
     int cta_threads = 512;  // threads per CTA of the staged K2 (tile geometry depends on it)
-    int variant = 0;      // 0 auto, 1 CTA-staged, 2 direct, 3 warp-pipelined
+    int variant = 0;      // 0 auto, 1 CTA-staged, 2 direct, 3 warp-pipelined, 4 row groups, 5 class layout
 
     // EM state
     double* theta = nullptr;   // M + 1
@@ -213,6 +232,12 @@ int em_launch_estep(rsem_b200_ctx* ctx, bool write_post);
 int em_launch_theta_update(rsem_b200_ctx* ctx, double n0, int round, int min_round, int max_round, int stats_slot);
 int em_max_degree(rsem_b200_ctx* ctx, uint32_t* max_deg);
 int em_make_abs_sid(rsem_b200_ctx* ctx);
+
+// class_kernels.cu
+void class_free(rsem_b200_ctx* ctx);
+int class_build(rsem_b200_ctx* ctx);
+int class_fill_vals(rsem_b200_ctx* ctx);
+int class_launch_estep(rsem_b200_ctx* ctx);
 
 // model_kernels.cu
 int model_launch_conprb(rsem_b200_ctx* ctx);

@@ -1199,7 +1199,7 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
     // Tile geometry follows the kernel that will consume the tiles.  Measured on C3 (ms per round):
     //   row-group kernel (variants 0 / 4): 3.40 with 1024 threads x 1 CTA per SM, 3.50 with 512 x 2, 3.75 with 256 x 4
     //   three-phase kernel (variant 1):    4.35 with 256 x 4, 4.39 with 128 x 8, 4.61 with 512 x 2
-    ctx->tiles_for_rows = ctx->variant == 0 || ctx->variant == 4;
+    ctx->tiles_for_rows = ctx->variant == 0 || ctx->variant == 4 || ctx->variant == 5;
     if (ctx->tiles_for_rows) ctx->cta_threads = 1024;
     else ctx->cta_threads = ctx->max_deg <= 256 ? 256 : 512;
     if (const char* e = getenv("RSEM_B200_CTA_THREADS")) {  // tuning knob
@@ -1282,7 +1282,40 @@ int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
         a.theta_tex = ctx->theta_tex;
     }
     if (ctx->N == 0) return 0;
-    if (ctx->tiles_for_rows != (ctx->variant == 0 || ctx->variant == 4)) {  // variant changed after the upload
+    // frozen-conprb rounds: equivalence-class layout (class_kernels.cu), built on first use after an upload and
+    // re-gathered when conprb changed; posterior write-back stays on the CSR stream (hit order)
+    static const int no_class = getenv("RSEM_B200_NO_CLASS") ? atoi(getenv("RSEM_B200_NO_CLASS")) : 0;
+    if (!write_post && (ctx->variant == 5 || (ctx->variant == 0 && !no_class))) {
+        if (!ctx->cls.built) {
+            if (int rc = class_build(ctx)) return rc;
+        }
+        if (ctx->cls.built) {
+            if (ctx->cls.vals_epoch != ctx->conprb_epoch) {
+                if (int rc = class_fill_vals(ctx)) return rc;
+            }
+            cudaEvent_t c0 = nullptr, c1 = nullptr;
+            if (ctx->profiling) {
+                if (ctx->ev_used == ctx->ev_pool.size()) {
+                    cudaEvent_t x, y;
+                    RB_CUDA(cudaEventCreate(&x));
+                    RB_CUDA(cudaEventCreate(&y));
+                    ctx->ev_pool.emplace_back(x, y);
+                }
+                c0 = ctx->ev_pool[ctx->ev_used].first;
+                c1 = ctx->ev_pool[ctx->ev_used].second;
+                ctx->ev_used++;
+                RB_CUDA(cudaEventRecord(c0, ctx->stream));
+            }
+            if (int rc = class_launch_estep(ctx)) return rc;
+            if (ctx->profiling) RB_CUDA(cudaEventRecord(c1, ctx->stream));
+            return 0;
+        }
+        if (ctx->variant == 5) {
+            set_error("class-layout E-step requested but the matrix is outside its limits (>= 2^32 reads or >= 2^40 hits)");
+            return RSEM_B200_ERR_UNSUPPORTED;
+        }
+    }
+    if (ctx->tiles_for_rows != (ctx->variant == 0 || ctx->variant == 4 || ctx->variant == 5)) {  // variant changed after the upload
         if (int rc = em_build_tiles(ctx)) return rc;
         a.tile_row = reinterpret_cast<const unsigned long long*>(ctx->tile_row);
         a.tile_hit = reinterpret_cast<const unsigned long long*>(ctx->tile_hit);

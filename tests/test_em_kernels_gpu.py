@@ -42,7 +42,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("case", CASES)
 def test_em_rounds_match_oracle(ctx, oracle, case, variant):
     N, M, deg, zipf, family, zero_rows = case
@@ -54,8 +54,8 @@ def test_em_rounds_match_oracle(ctx, oracle, case, variant):
     ctx.upload_conprb(conprb, ncpv)
     ctx.set_theta(theta0)
     if zero_rows > 0 and variant in (1, 3, 4):
-        # rows without hits are legal at the C ABI but never produced by rsem-parse-alignments; only the
-        # direct kernel handles them and asking for the staged one must fail loudly
+        # rows without hits are legal at the C ABI but never produced by rsem-parse-alignments; the class layout
+        # (variants 0 / 5) and the direct kernel handle them, asking for a staged CSR kernel must fail loudly
         from rsem_b200 import RsemB200Error
         with pytest.raises(RsemB200Error):
             ctx.em_rounds(1, 7, 20, 10000, n0)
@@ -90,7 +90,7 @@ def test_expected_weights(ctx, oracle):
     row_ptr, sid, conprb, ncpv = synth.random_matrix(8000, 700, 8, seed=9)
     theta = np.random.default_rng(1).random(701)
     theta /= theta.sum()
-    for variant in (1, 2, 3, 4):
+    for variant in (0, 1, 2, 3, 4):
         ctx.set_estep_variant(variant)
         ctx.upload_hits(row_ptr, sid, 700)
         ctx.upload_conprb(conprb, ncpv)
@@ -116,8 +116,9 @@ def test_all_rows_below_epsilon(ctx):
     assert np.array_equal(ctx.get_theta(), np.array([1.0, 0.0, 0.0]))
 
 
-def test_rows_longer_than_a_stage_use_the_unstaged_kernel(ctx, oracle):
-    """a 6000-hit row does not fit a shared-memory stage: auto must fall back to the direct kernel and stay exact"""
+def test_rows_longer_than_a_stage_get_their_own_launch(ctx, oracle):
+    """a 6000-hit row does not fit a shared-memory stage: the class layout leaves it to the long-row launch (frozen
+    rounds), the posterior pass falls back to the unstaged kernel; both stay exact"""
     rng = np.random.default_rng(3)
     row_ptr, sid, conprb, ncpv = synth.random_matrix(3000, 8000, 7, seed=21)
     # splice one very long row into the middle
@@ -141,6 +142,96 @@ def test_rows_longer_than_a_stage_use_the_unstaged_kernel(ctx, oracle):
     ctx.em_rounds(1, 5, 20, 10000, n0)
     theta_ref, _, _ = oracle.em_rounds(row_ptr, sid, conprb, ncpv, theta0, n0, 1, 5, 20, 10000)
     _check_theta(ctx.get_theta(), theta_ref)
+    info = ctx.class_layout_info()
+    assert info["built"] == 1 and info["long_rows"] == 1 and info["rows"] == N - 1
+    counts = ctx.expected_weights()
+    c_ref, _, _ = oracle.estep(row_ptr, sid, conprb, ncpv, ctx.get_theta(), want_post=True)
+    assert np.allclose(counts, c_ref, rtol=1e-10, atol=1e-13)
+
+
+def _class_matrix(N, M, deg, seed, dup, zipf=False):
+    """rows drawn from a pool of N / dup distinct transcript lists (equivalence classes of ~dup reads), shuffled,
+    with independent conprb per read - the structure the class layout exploits"""
+    rng = np.random.default_rng(seed)
+    pool_rp, pool_sid, _, _ = synth.random_matrix(max(1, N // dup), M, deg, seed=seed + 1, zipf=zipf)
+    pool_rp = pool_rp.astype(np.int64)
+    pick = rng.integers(0, len(pool_rp) - 1, size=N)
+    degs = (pool_rp[pick + 1] - pool_rp[pick])
+    row_ptr = np.zeros(N + 1, np.uint64)
+    row_ptr[1:] = np.cumsum(degs)
+    H = int(row_ptr[-1])
+    src = np.repeat(pool_rp[pick], degs) + (np.arange(H) - np.repeat(row_ptr[:-1].astype(np.int64), degs))
+    sid = np.abs(pool_sid[src]) * np.where(rng.random(H) < 0.5, 1, -1).astype(np.int32)  # strands differ inside a class
+    conprb = 10.0 ** rng.uniform(-60, -3, size=H)
+    conprb[rng.random(H) < 0.02] = 10.0 ** rng.uniform(-320, -295, size=1)
+    conprb[rng.random(H) < 0.01] = 0.0
+    ncpv = 10.0 ** rng.uniform(-80, -40, size=N)
+    ncpv[rng.random(N) < 0.05] = 0.0
+    return row_ptr, sid.astype(np.int32), conprb, ncpv
+
+
+CLASS_CASES = [
+    # N, M, deg, dup, zipf, rows per segment, CTA threads
+    (40000, 3000, 20, 12, False, 8, 1024),     # C3-like: classes of ~12 reads
+    (40000, 3000, 20, 12, False, 8, 512),
+    (40000, 3000, 20, 200, False, 16, 1024),   # large classes: one-class batches, folded reductions
+    (60000, 500, 2, 300, False, 8, 1024),      # degree <= 4: thread per segment
+    (30000, 4000, 6, 1, False, 8, 1024),       # hardly any duplicates: segments of one row
+    (30000, 3000, 40, 20, False, 3, 512),      # 16 lanes per segment, odd segment size
+    (20000, 6000, 100, 10, False, 8, 1024),    # 32 lanes per segment
+    (50000, 2000, 0, 30, True, 8, 1024),       # Zipf degrees 1..200 (C5 shape)
+]
+
+
+@pytest.mark.parametrize("case", CLASS_CASES)
+def test_class_layout_matches_oracle(ctx, oracle, case, monkeypatch):
+    """variant 5 (equivalence-class layout) on matrices with real class structure, every lane-group configuration"""
+    N, M, deg, dup, zipf, seg_rows, threads = case
+    monkeypatch.setenv("RSEM_B200_CLASS_ROWS", str(seg_rows))
+    monkeypatch.setenv("RSEM_B200_CLASS_THREADS", str(threads))
+    row_ptr, sid, conprb, ncpv = _class_matrix(N, M, deg, seed=N + deg, dup=dup, zipf=zipf)
+    n0 = N / 20
+    theta0 = synth.init_theta(M, n0, N + n0)
+    ctx.set_estep_variant(5)
+    ctx.upload_hits(row_ptr, sid, M)
+    ctx.upload_conprb(conprb, ncpv)
+    ctx.set_theta(theta0)
+    stats, _ = ctx.em_rounds(1, 6, 20, 10000, n0)
+    info = ctx.class_layout_info()
+    assert info["built"] == 1 and info["rows"] == N and info["vals"] == int(row_ptr[-1]) + N
+    if dup >= 10:
+        assert info["segments"] < N / 2  # classes were found
+    theta_ref, stats_ref, _ = oracle.em_rounds(row_ptr, sid, conprb, ncpv, theta0, n0, 1, 6, 20, 10000)
+    _check_theta(ctx.get_theta(), theta_ref)
+    for (s, b, t), (s2, b2, t2) in zip(stats, stats_ref):
+        assert abs(s - s2) <= 1e-9 * s2
+        assert abs(t - t2) <= 2
+    # conprb changes (a model round in the executable): the value stream must be re-gathered
+    conprb2 = conprb[::-1].copy()
+    ctx.upload_conprb(conprb2, ncpv)
+    ctx.set_theta(theta0)
+    ctx.em_rounds(1, 3, 20, 10000, n0)
+    theta_ref, _, _ = oracle.em_rounds(row_ptr, sid, conprb2, ncpv, theta0, n0, 1, 3, 20, 10000)
+    _check_theta(ctx.get_theta(), theta_ref)
+    ctx.set_estep_variant(0)
+
+
+def test_class_layout_c5_shape_one_million_reads(ctx, oracle):
+    """BASELINE configs[4] shape at a size the oracle finishes in seconds: Zipf(1.1) degrees capped at 200, 1 M reads,
+    every kernel variant against the oracle"""
+    N, M = 1_000_000, 40_000
+    row_ptr, sid, conprb, ncpv = _class_matrix(N, M, 0, seed=5, dup=25, zipf=True)
+    n0 = N / 20
+    theta0 = synth.init_theta(M, n0, N + n0)
+    theta_ref, _, _ = oracle.em_rounds(row_ptr, sid, conprb, ncpv, theta0, n0, 1, 4, 20, 10000, n_threads=16)
+    for variant in (5, 4, 1):
+        ctx.set_estep_variant(variant)
+        ctx.upload_hits(row_ptr, sid, M)
+        ctx.upload_conprb(conprb, ncpv)
+        ctx.set_theta(theta0)
+        ctx.em_rounds(1, 4, 20, 10000, n0)
+        _check_theta(ctx.get_theta(), theta_ref)
+    ctx.set_estep_variant(0)
 
 
 @pytest.mark.parametrize("threads", [128, 256, 512, 1024])
