@@ -114,6 +114,11 @@ int rsem_b200_ctx_device_bytes(rsem_b200_ctx* ctx, uint64_t* bytes);
 int rsem_b200_comm_unique_id(void* id_out /* 128 bytes */);
 int rsem_b200_comm_init(rsem_b200_ctx* ctx, const void* id /* 128 bytes */, int n_ranks, int rank);
 
+/* Read sharding over GPUs = the reference's read sharding over threads (init<>, EM.cpp:135-157): shard i gets the
+ * contiguous reads [bounds[i], bounds[i + 1]) holding about nHits / n_shards hits, every shard at least one read while
+ * reads are left.  Pure host arithmetic (no device needed); bounds has n_shards + 1 entries.                      */
+int rsem_b200_shard_reads(uint64_t N, const uint64_t* row_ptr /* N + 1 */, int32_t n_shards, uint64_t* bounds);
+
 /* ---- data upload ------------------------------------------------------------------------------
  * Hit buffer = HitContainer<SingleHit|PairedEndHit> (HitContainer.h:12-59) as SoA CSR.
  * row_ptr has N + 1 entries, row_ptr[0] = 0, row_ptr[N] = H.  insertL may be NULL (single-end).

@@ -76,7 +76,7 @@ SYMBOLS = [
     "rsem_b200_set_model", "rsem_b200_calc_conprb", "rsem_b200_set_theta", "rsem_b200_get_theta",
     "rsem_b200_em_rounds", "rsem_b200_em_model_round", "rsem_b200_expected_weights", "rsem_b200_gibbs_upload",
     "rsem_b200_gibbs_run", "rsem_b200_launch_count", "rsem_b200_estep_timing", "rsem_b200_set_profiling",
-    "rsem_b200_set_estep_variant", "rsem_b200_class_layout_info",
+    "rsem_b200_set_estep_variant", "rsem_b200_class_layout_info", "rsem_b200_shard_reads",
 ]
 
 
@@ -102,6 +102,14 @@ class Lib:
         n = C.c_int(0)
         self.check(self.dll.rsem_b200_device_count(C.byref(n)))
         return n.value
+
+    def shard_reads(self, row_ptr, n_shards: int):
+        """-> [(first_read, last_read_exclusive)] per shard, the reference's thread-sharding rule (EM.cpp:135-157)"""
+        row_ptr = _arr(row_ptr, np.uint64)
+        bounds = np.zeros(n_shards + 1, np.uint64)
+        self.check(self.dll.rsem_b200_shard_reads(C.c_uint64(len(row_ptr) - 1), _p(row_ptr, C.c_uint64), C.c_int32(n_shards),
+                                                  _p(bounds, C.c_uint64)))
+        return [(int(bounds[i]), int(bounds[i + 1])) for i in range(n_shards)]
 
     def comm_unique_id(self) -> bytes:
         buf = C.create_string_buffer(128)

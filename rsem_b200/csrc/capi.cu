@@ -257,6 +257,31 @@ int rsem_b200_comm_init(rsem_b200_ctx* c, const void* id, int n_ranks, int rank)
     return nccl_comm_init(&c->comm, id, n_ranks, rank);
 }
 
+int rsem_b200_shard_reads(uint64_t N, const uint64_t* row_ptr, int32_t n_shards, uint64_t* bounds) {
+    RB_ARG(row_ptr && bounds, "NULL argument");
+    RB_ARG(n_shards >= 1, "n_shards must be >= 1");
+    // EM.cpp:135-157: worker i takes reads until it holds >= nHits / nThreads hits, while one read is left for every
+    // later worker; the last worker takes the rest.  More shards than reads: the surplus shards stay empty (the
+    // reference clamps nThreads to N1 instead, EM.cpp:640).
+    const uint64_t world = std::min<uint64_t>((uint64_t)n_shards, std::max<uint64_t>(N, 1));
+    const uint64_t thr = row_ptr[N] / world;
+    uint64_t cur = 0;
+    bounds[0] = 0;
+    for (uint64_t i = 0; i < world; ++i) {
+        uint64_t end = N;
+        if (i != world - 1) {
+            const uint64_t left = world - i - 1, target = row_ptr[cur] + thr;
+            end = (uint64_t)(std::lower_bound(row_ptr, row_ptr + N + 1, target) - row_ptr);
+            if (end < cur) end = cur;
+            if (end > N - left) end = N - left;
+        }
+        bounds[i + 1] = end;
+        cur = end;
+    }
+    for (uint64_t i = world; i < (uint64_t)n_shards; ++i) bounds[i + 1] = N;
+    return 0;
+}
+
 int rsem_b200_upload_hits(rsem_b200_ctx* c, uint64_t N, uint64_t H, int32_t M, const uint64_t* row_ptr,
                           const int32_t* sid, const int32_t* pos, const int32_t* insertL) {
     RB_ARG(c && row_ptr && (sid || H == 0), "NULL argument");

@@ -26,7 +26,9 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <ctime>
 
 #include "common.cuh"
 
@@ -673,6 +675,27 @@ struct Scratch {  // frees its buffers on every exit path
 
 inline unsigned blocks_for(unsigned long long n, unsigned per_block) { return (unsigned)((n + per_block - 1) / per_block); }
 
+struct PhaseTimer {  // RSEM_B200_CLASS_TIMING=1: wall-clock per build phase on stderr (syncs the stream; diagnostics only)
+    cudaStream_t st;
+    bool on;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    }
+    explicit PhaseTimer(cudaStream_t s) : st(s), on(getenv("RSEM_B200_CLASS_TIMING") != nullptr), t0(0) {
+        if (on) { cudaStreamSynchronize(st); t0 = now(); }
+    }
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const double t = now();
+        fprintf(stderr, "rsem_b200 class layout: %8.3f ms  %s\n", (t - t0) * 1e3, what);
+        t0 = t;
+    }
+};
+
 }  // namespace
 
 void class_free(rsem_b200_ctx* ctx) {
@@ -698,6 +721,7 @@ int class_build(rsem_b200_ctx* ctx) {
         if (v >= 1 && v <= 255) R = (unsigned)v;
     }
     Scratch sc;
+    PhaseTimer pt(st);
     // ---- 1. row keys, sorted
     unsigned long long *keys = nullptr, *keys_s = nullptr;
     unsigned *rows0 = nullptr, *rows_s = nullptr, *d_cnt = nullptr;
@@ -727,6 +751,7 @@ int class_build(rsem_b200_ctx* ctx) {
     RB_CUDA(cudaStreamSynchronize(st));
     const unsigned n_long = h_cnt[0];
     const unsigned n_rows = (unsigned)(N - n_long);
+    pt.mark("row keys + sort by (degree, hash)");
     sc.release(keys); keys = nullptr;
     sc.release(rows0); rows0 = nullptr;
     L.n_long = n_long;
@@ -767,6 +792,7 @@ int class_build(rsem_b200_ctx* ctx) {
     RB_CUDA(cudaStreamSynchronize(st));
     sc.release(a32); sc.release(b32); sc.release(c32);
     a32 = b32 = c32 = nullptr;
+    pt.mark("classes verified, segments cut");
     // ---- 3. segments ordered by (degree, rows), batches of 32 / G equal segments
     RB_CUDA(sc.alloc(&key2, n_segs));
     RB_CUDA(sc.alloc(&key2_s, n_segs));
@@ -829,6 +855,7 @@ int class_build(rsem_b200_ctx* ctx) {
         set_error("class layout: a batch does not fit a shared-memory stage (internal limit)");
         return RSEM_B200_ERR_UNSUPPORTED;
     }
+    pt.mark("segments sorted, batches formed");
     L.n_vals = totals[0];
     L.n_ids = totals[1];
     L.n_segs = n_segs;
@@ -878,6 +905,7 @@ int class_build(rsem_b200_ctx* ctx) {
     RB_CUDA(cudaMalloc(&L.vals, ((size_t)L.n_vals + 32) * sizeof(double)));
     RB_CUDA(cudaMemsetAsync(L.vals + L.n_vals, 0, 32 * sizeof(double), st));
     RB_CUDA(cudaStreamSynchronize(st));
+    pt.mark("tiles, descriptors, ids");
     sc.keep(rows_s);
     L.rows = rows_s;
     L.R = R;
@@ -895,6 +923,7 @@ int class_build(rsem_b200_ctx* ctx) {
 int class_fill_vals(rsem_b200_ctx* ctx) {
     ClassLayout& L = ctx->cls;
     if (!L.built) return 0;
+    PhaseTimer pt(ctx->stream);
     if (L.n_batches) {
         cls_fill_vals_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(
             reinterpret_cast<const unsigned long long*>(ctx->row_ptr), ctx->conprb, ctx->ncpv,
@@ -902,6 +931,7 @@ int class_fill_vals(rsem_b200_ctx* ctx) {
         RB_CUDA(cudaGetLastError());
         ctx->launches++;
     }
+    pt.mark("value stream gathered from conprb / ncpv");
     L.vals_epoch = ctx->conprb_epoch;
     return 0;
 }

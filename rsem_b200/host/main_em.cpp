@@ -71,24 +71,13 @@ void print_round(int round, const rsem_b200_round_stats& s) {
     }
 }
 
-// Contiguous read ranges with about nHits / world hits each: the greedy rule the reference uses for its threads
-// (EM.cpp:135-157; same as rsem_b200/sharding.py, tested against the reference's own "Thread i : N = .." lines).
+// Contiguous read ranges with about nHits / world hits each: the reference's thread-sharding rule (EM.cpp:135-157),
+// implemented once in the library (rsem_b200_shard_reads) so that bench.py and the tests exercise the same code.
 std::vector<std::pair<uint64_t, uint64_t>> shard_reads(const std::vector<uint64_t>& row_ptr, int world) {
-    const uint64_t n = row_ptr.size() - 1, thr = row_ptr[n] / (uint64_t)world;
+    std::vector<uint64_t> bounds((size_t)world + 1);
+    check_rc(rsem_b200_shard_reads(row_ptr.size() - 1, row_ptr.data(), world, bounds.data()), "shard_reads");
     std::vector<std::pair<uint64_t, uint64_t>> out;
-    uint64_t cur = 0;
-    for (int i = 0; i < world; ++i) {
-        const uint64_t left = (uint64_t)(world - i - 1);
-        uint64_t end = n;
-        if (i != world - 1) {
-            const uint64_t target = row_ptr[cur] + thr;
-            end = (uint64_t)(std::lower_bound(row_ptr.begin(), row_ptr.end(), target) - row_ptr.begin());
-            if (end < cur) end = cur;
-            if (end > n - left) end = n - left;
-        }
-        out.emplace_back(cur, end);
-        cur = end;
-    }
+    for (int i = 0; i < world; ++i) out.emplace_back(bounds[i], bounds[i + 1]);
     return out;
 }
 

@@ -12,7 +12,18 @@ import torch.multiprocessing as mp
 
 import rsem_files as rf
 import synth
-from rsem_b200.sharding import shard_reads, slice_csr
+import rsem_b200
+
+
+def shard_reads(row_ptr, n):
+    """the library's rule (rsem_b200_shard_reads, host arithmetic: no GPU needed) - the one rsem-run-em and bench.py use"""
+    return rsem_b200.load_library().shard_reads(row_ptr, n)
+
+
+def slice_csr(row_ptr, first, last):
+    row_ptr = np.asarray(row_ptr, dtype=np.uint64)
+    h0, h1 = int(row_ptr[first]), int(row_ptr[last])
+    return (row_ptr[first:last + 1] - np.uint64(h0)).astype(np.uint64), h0, h1
 
 
 @pytest.mark.parametrize("threads", [2, 3, 7])
@@ -32,8 +43,11 @@ def test_shards_edge_cases():
     assert shard_reads(rp, 1) == [(0, 4)]
     parts = shard_reads(rp, 4)
     assert [b - a for a, b in parts] == [1, 1, 1, 1]
-    parts = shard_reads(rp, 9)  # more ranks than reads: clamped like the reference (EM.cpp:640)
-    assert parts[-1][1] == 4 and all(b >= a for a, b in parts)
+    parts = shard_reads(rp, 9)  # more shards than reads: the surplus shards are empty (the reference clamps, EM.cpp:640)
+    assert parts[:4] == shard_reads(rp, 4) and all(p == (4, 4) for p in parts[4:])
+    # a heavy first read: the first shard stops right after it, the middle shard takes reads until one is left for the last
+    rp = np.array([0, 100, 101, 102, 103], np.uint64)
+    assert shard_reads(rp, 3) == [(0, 1), (1, 3), (3, 4)]
 
 
 def _worker(rank, world, port, tmp):
