@@ -130,7 +130,8 @@ int rsem_b200_upload_hits(rsem_b200_ctx* ctx, uint64_t N, uint64_t H, int32_t M,
 int rsem_b200_upload_conprb(rsem_b200_ctx* ctx, const double* conprb, const double* ncpv);
 int rsem_b200_download_conprb(rsem_b200_ctx* ctx, double* conprb, double* ncpv);
 /* Same as upload_hits + upload_conprb but from DEVICE pointers already resident on ctx's GPU
- * (no copy across PCIe; buffers are copied device-to-device into the context).                 */
+ * (no copy across PCIe; buffers are copied device-to-device into the context, on the context's
+ * stream: work that produces them on another stream must have completed before the call).      */
 int rsem_b200_adopt_device_matrix(rsem_b200_ctx* ctx, uint64_t N, uint64_t H, int32_t M, const uint64_t* d_row_ptr,
                                   const int32_t* d_sid, const double* d_conprb, const double* d_ncpv);
 
@@ -237,6 +238,9 @@ int rsem_b200_set_estep_variant(rsem_b200_ctx* ctx, int32_t variant);
  * out[8] = { built (0/1), rows in the layout, rows handled by the long-row launch, segments, batches, tiles,
  *            staged doubles (conprb + ncpv), staged ids }.  Streamed bytes per round = 8 out[6] + 4 out[7] + 16 out[4]. */
 int rsem_b200_class_layout_info(rsem_b200_ctx* ctx, uint64_t* out /* 8 */);
+/* Busy time (ns, %globaltimer) of every persistent CTA in the latest class-layout E-step launch: the evidence for
+ * the segmented reduction's load balance on skewed matrices (BASELINE configs[4]).  *n = CTAs written (<= cap).   */
+int rsem_b200_estep_cta_times(rsem_b200_ctx* ctx, uint64_t* out_ns, int32_t cap, int32_t* n);
 
 #ifdef __cplusplus
 }

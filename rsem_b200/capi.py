@@ -77,6 +77,7 @@ SYMBOLS = [
     "rsem_b200_em_rounds", "rsem_b200_em_model_round", "rsem_b200_expected_weights", "rsem_b200_gibbs_upload",
     "rsem_b200_gibbs_run", "rsem_b200_launch_count", "rsem_b200_estep_timing", "rsem_b200_set_profiling",
     "rsem_b200_set_estep_variant", "rsem_b200_class_layout_info", "rsem_b200_shard_reads",
+    "rsem_b200_estep_cta_times",
 ]
 
 
@@ -288,6 +289,12 @@ class Context:
         d = dict(zip(keys, (int(x) for x in out)))
         d["bytes_per_round"] = 8 * d["vals"] + 4 * d["ids"] + 16 * d["batches"]
         return d
+
+    def estep_cta_times(self) -> np.ndarray:
+        out = np.zeros(1024, np.uint64)
+        n = C.c_int32(0)
+        self.lib.check(self.lib.dll.rsem_b200_estep_cta_times(self._h, _p(out, C.c_uint64), C.c_int32(1024), C.byref(n)))
+        return out[: n.value]
 
     def set_estep_variant(self, v: int):
         self.lib.check(self.lib.dll.rsem_b200_set_estep_variant(self._h, C.c_int32(v)))

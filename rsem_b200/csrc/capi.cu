@@ -195,6 +195,10 @@ int rsem_b200_ctx_create(int device, rsem_b200_ctx** out) {
     RB_CUDA(cudaMalloc(&c->err_flag, sizeof(int)));
     RB_CUDA(cudaMemset(c->done_flag, 0, sizeof(int)));
     RB_CUDA(cudaMemset(c->err_flag, 0, sizeof(int)));
+    if (getenv("RSEM_B200_PHASE_TIMING")) {
+        c->phase_timing = true;
+        for (auto& e : c->ph_ev) RB_CUDA(cudaEventCreate(&e));
+    }
     *out = c;
     return 0;
 }
@@ -204,6 +208,14 @@ int rsem_b200_ctx_destroy(rsem_b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->comm) nccl_comm_destroy(c->comm);
+    if (c->phase_timing) {
+        static const char* names[3] = {"K1 conprb_kernel", "K2 E-step with posteriors", "K3 model statistics"};
+        for (int i = 0; i < 3; ++i)
+            if (c->ph_n[i])
+                fprintf(stderr, "rsem_b200 phase timing: %-28s %9.3f ms per launch over %llu launches (device %d)\n", names[i],
+                        c->ph_ms[i] / (double)c->ph_n[i], (unsigned long long)c->ph_n[i], c->device);
+        for (auto& e : c->ph_ev) cudaEventDestroy(e);
+    }
     free_hits(c);
     free_reads(c);
     free_refs(c);
@@ -529,17 +541,24 @@ int rsem_b200_em_model_round(rsem_b200_ctx* c, double n0, rsem_b200_model_stats*
     RB_ARG(c->row_ptr && c->pos && c->model_set && c->reads.n_mates > 0 && c->refs.M > 0,
            "hits (with positions), model, reads and refs must be uploaded first");
     RB_CUDA(cudaSetDevice(c->device));
+    const bool pt = c->phase_timing;
+    bool ran_k1 = false;
+    if (pt) RB_CUDA(cudaEventRecord(c->ph_ev[0], c->stream));
     if (!c->conprb_valid) {
         if (int rc = rsem_b200_calc_conprb(c)) return rc;
+        ran_k1 = true;
     }
     if (int rc = ensure_post(c)) return rc;
     if (int rc = ensure_stats(c, 1)) return rc;
     RB_CUDA(cudaMemsetAsync(c->done_flag, 0, sizeof(int), c->stream));
+    if (pt) RB_CUDA(cudaEventRecord(c->ph_ev[1], c->stream));
     if (int rc = em_launch_estep(c, true)) return rc;
+    if (pt) RB_CUDA(cudaEventRecord(c->ph_ev[2], c->stream));
     // K3 needs the (local) posteriors; statistics buffer layout is set up by model_launch_update
     c->stats.gld_lb = stats->gld_lb;
     c->stats.gld_span = stats->gld_span;
     if (int rc = model_launch_update(c)) return rc;
+    if (pt) RB_CUDA(cudaEventRecord(c->ph_ev[3], c->stream));
     if (c->comm) {
         if (int rc = nccl_allreduce_sum_f64(c->comm, c->count, (size_t)c->M + 1, c->stream)) return rc;
         if (int rc = nccl_allreduce_sum_f64(c->comm, c->stats_buf, c->stats.total_doubles, c->stream)) return rc;
@@ -559,6 +578,13 @@ int rsem_b200_em_model_round(rsem_b200_ctx* c, double n0, rsem_b200_model_stats*
         RB_CUDA(cudaMemcpyAsync(stats->rspd_pdf, c->stats.rspd_pdf, ((size_t)c->model.rspd_B + 2) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));
     harvest_events(c);
+    if (pt) {
+        for (int i = 0; i < 3; ++i) {
+            if (i == 0 && !ran_k1) continue;
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, c->ph_ev[i], c->ph_ev[i + 1]) == cudaSuccess) { c->ph_ms[i] += ms; c->ph_n[i]++; }
+        }
+    }
     return check_err_flag(c);
 }
 
@@ -644,6 +670,19 @@ int rsem_b200_class_layout_info(rsem_b200_ctx* c, uint64_t* out) {
     out[5] = L.n_tiles;
     out[6] = L.n_vals;
     out[7] = L.n_ids;
+    return 0;
+}
+
+int rsem_b200_estep_cta_times(rsem_b200_ctx* c, uint64_t* out_ns, int32_t cap, int32_t* n) {
+    RB_ARG(c && out_ns && n, "NULL argument");
+    *n = 0;
+    const ClassLayout& L = c->cls;
+    if (!L.cta_ns || L.last_grid == 0) return 0;
+    RB_CUDA(cudaSetDevice(c->device));
+    const int k = std::min<int>(cap, (int)L.last_grid);
+    RB_CUDA(cudaMemcpyAsync(out_ns, L.cta_ns, (size_t)k * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    *n = k;
     return 0;
 }
 

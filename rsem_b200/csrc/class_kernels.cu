@@ -43,14 +43,17 @@ constexpr unsigned kMaxBatchVals = 4096;  // values (conprb + ncpv) per batch, s
 constexpr unsigned long long kLongKey = 1ull << 59;
 constexpr unsigned long long kOff48 = (1ull << 48) - 1, kOff40 = (1ull << 40) - 1;
 
-// lanes per segment (G) and register slots per lane (S) from the degree: S * G >= d up to d = 128
+// A row of degree d has d + 1 columns: its d hits and the noise entry (theta[0] * ncpv, EM.cpp:210-213), which is
+// stored and processed as the last column.  Lanes per segment (G) and register slots per lane (S) from the column
+// count w: S * G >= w up to w = 128.
 __host__ __device__ __forceinline__ unsigned group_of_deg(unsigned d) {
-    return d <= 4 ? 1u : d <= 8 ? 2u : d <= 16 ? 4u : d <= 32 ? 8u : d <= 64 ? 16u : 32u;
+    const unsigned w = d + 1u;
+    return w <= 4 ? 1u : w <= 8 ? 2u : w <= 16 ? 4u : w <= 32 ? 8u : w <= 64 ? 16u : 32u;
 }
 __host__ __device__ __forceinline__ unsigned cfg_of_deg(unsigned d) {  // 2 * log2(G) + (S == 4)
     const unsigned G = group_of_deg(d);
     const unsigned lg = G == 1 ? 0u : G == 2 ? 1u : G == 4 ? 2u : G == 8 ? 3u : G == 16 ? 4u : 5u;
-    return 2u * lg + (d > 3u * G ? 1u : 0u);
+    return 2u * lg + (d + 1u > 3u * G ? 1u : 0u);
 }
 __host__ __device__ __forceinline__ unsigned rows_cap(unsigned d, unsigned R) {
     const unsigned P = 32u / group_of_deg(d);
@@ -298,8 +301,7 @@ __global__ void cls_fill_ids_kernel(const unsigned long long* __restrict__ rp, c
     }
 }
 
-// one warp per batch: ncpv of (segment gi, row r) at val_off + r nsb + gi, conprb of column c at
-// val_off + nsb n + (r d + c) nsb + gi
+// one warp per batch: value (segment gi, row r, column c) at val_off + (r (d + 1) + c) nsb + gi; column d is the row's ncpv
 __global__ void cls_fill_vals_kernel(const unsigned long long* __restrict__ rp, const double* __restrict__ conprb,
                                      const double* __restrict__ ncpv, const BatchDesc* __restrict__ desc,
                                      const unsigned* __restrict__ batch_first, const unsigned* __restrict__ fseg_first,
@@ -311,19 +313,13 @@ __global__ void cls_fill_vals_kernel(const unsigned long long* __restrict__ rp, 
         const unsigned d = (unsigned)(bd.w0 >> 48), n = (unsigned)(bd.w1 >> 40) & 255u, nsb = (unsigned)(bd.w1 >> 48) & 255u;
         double* out = vals + (bd.w0 & kOff48);
         const unsigned f0 = batch_first[b];
-        const unsigned nr = nsb * n;
-        for (unsigned idx = lane; idx < nr; idx += 32) {
-            const unsigned gi = idx % nsb, r = idx / nsb;
-            out[idx] = ncpv[rows[fseg_first[f0 + gi] + r]];
-        }
-        out += nr;
         // lane -> (gi, column): consecutive lanes write consecutive doubles, each lane walks its own source row
-        const unsigned per_row = nsb * d;  // elements of one row-step of the batch
+        const unsigned per_row = nsb * (d + 1u);  // elements of one row-step of the batch
         for (unsigned r = 0; r < n; ++r)
             for (unsigned idx = lane; idx < per_row; idx += 32) {
                 const unsigned gi = idx % nsb, c = idx / nsb;
                 const unsigned row = rows[fseg_first[f0 + gi] + r];
-                out[(unsigned long long)r * per_row + idx] = conprb[rp[row] + c];
+                out[(unsigned long long)r * per_row + idx] = c < d ? conprb[rp[row] + c] : ncpv[row];
             }
     }
 }
@@ -351,6 +347,7 @@ struct ClassArgs {
     const double* theta;
     double* count;
     const int* done_flag;
+    unsigned long long* cta_ns;  // per-CTA busy time of this launch (globaltimer, ns): load-balance evidence
 };
 
 struct StageDesc {  // written by the producer when it issues a tile
@@ -358,20 +355,24 @@ struct StageDesc {  // written by the producer when it issues a tile
     unsigned long long id_base;
     unsigned o_ids, o_desc;       // byte offsets of the id and descriptor slices inside the stage
     unsigned n_batches;
+    unsigned first_batch_mod;     // (global index of the tile's first batch) % consumer warps
 };
 
-template <int T>
+template <int W>
 struct ClassSmem {
     __align__(128) unsigned char stage[kStages][kStageBytes];
-    unsigned long long full_bar[kStages];
+    unsigned long long full_bar[kStages];   // producer -> consumers: the stage's bytes have landed (complete_tx)
+    unsigned long long empty_bar[kStages];  // consumers -> producer: every consumer warp is done with the stage
     StageDesc sd[kStages];
-    unsigned next_batch[kStages];
-    unsigned warps_done[kStages];
-    double red[T / 32];
+    double red[W + 1];
 };
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void issue_class_tile(const ClassArgs& a, unsigned k, unsigned char* st, unsigned long long* bar,
-                                                 StageDesc& sd) {
+                                                 StageDesc& sd, unsigned n_consumers) {
     const TileRec t0 = a.tile[k], t1 = a.tile[k + 1];
     const unsigned long long vb = t0.val_begin & ~1ull, ib = t0.id_begin & ~3ull;
     const unsigned b_val = round16((unsigned)(t1.val_begin - vb) * 8u);
@@ -383,11 +384,16 @@ __device__ __forceinline__ void issue_class_tile(const ClassArgs& a, unsigned k,
     sd.o_ids = b_val;
     sd.o_desc = b_val + b_ids;
     sd.n_batches = nb;
+    sd.first_batch_mod = (unsigned)(t0.batch_begin % n_consumers);
     mbar_expect_tx(bar, b_val + b_ids + b_desc);
     if (b_val) bulk_load(st, a.vals + vb, b_val, bar);
     if (b_ids) bulk_load(st + b_val, a.ids + ib, b_ids, bar);
     bulk_load(st + b_val + b_ids, a.desc + t0.batch_begin, b_desc, bar);
 }
+
+#ifdef RB_CLASS_DEBUG
+__device__ int g_dbg_flag = 0;
+#endif
 
 template <int G>
 __device__ __forceinline__ double seg_sum(double v) {  // lanes of a segment are strided by P = 32 / G
@@ -398,104 +404,117 @@ __device__ __forceinline__ double seg_sum(double v) {  // lanes of a segment are
 template <>
 __device__ __forceinline__ double seg_sum<1>(double v) { return v; }
 
-// One batch: P = 32 / G segments of n rows x d columns; lane = g * P + gi owns columns g, g + G, ... of segment gi.
-// U rows are in flight per iteration (instruction-level parallelism across the dependent load -> product -> row sum ->
-// reciprocal chain).
+// 1 / x for a normal, positive x: hardware seed (about 20 bits) + two Newton steps.  The row sums are >= 1e-300 and
+// far below overflow, so none of the special cases of a full fp64 division can occur; the result is within one ulp
+// of the correctly rounded reciprocal (the weights f / sum are formed as f * (1 / sum): EM.cpp:231 divides instead,
+// parity is checked at 1e-9 relative on theta).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// U rows of a batch at once.  ROWS_OK: all U rows exist (main loop) - otherwise rows >= n_left are idle (remainder).
+template <int G, int S, int U, bool ROWS_OK>
+__device__ __forceinline__ void batch_rows(const double* __restrict__ cr, unsigned row_stride, unsigned n_left,
+                                           const double (&th)[S], const bool (&col_ok)[S], const unsigned (&coff)[S],
+                                           double (&acc)[S], bool tail, unsigned g, unsigned w, unsigned nsb, unsigned d,
+                                           const int* __restrict__ bi, unsigned ids_stride, unsigned ids_gi, bool seg_ok,
+                                           const double* __restrict__ theta, double* count, double& acc0) {
+    double x[U][S], part[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool row_ok = ROWS_OK || (unsigned)u < n_left;
+#pragma unroll
+        for (int q = 0; q < S; ++q) {
+            double c = 0.0;  // idle lanes must not read: the bytes behind a batch are arbitrary (possibly NaN patterns)
+            if (col_ok[q] && row_ok) c = cr[u * row_stride + coff[q]];
+            x[u][q] = th[q] * c;
+            if (x[u][q] < kEpsilon) x[u][q] = 0.0;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (S == 4) part[u] = (x[u][0] + x[u][1]) + (x[u][2] + x[u][3]);
+        else part[u] = (x[u][0] + x[u][1]) + x[u][2];
+    }
+    if (tail && seg_ok) {  // columns beyond G * S (rows with more than 127 hits): not kept in registers
+        for (unsigned c = g + G * S; c < w; c += G) {
+            const double thc = __ldg(theta + (c < d ? bi[c * ids_stride + ids_gi] : 0));
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (ROWS_OK || (unsigned)u < n_left) {
+                    double f = thc * cr[u * row_stride + c * nsb];
+                    if (f < kEpsilon) f = 0.0;
+                    part[u] += f;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) part[u] = seg_sum<G>(part[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const double inv = part[u] >= kEpsilon ? fast_rcp(part[u]) : 0.0;  // idle rows: part = 0 -> inv = 0
+#pragma unroll
+        for (int q = 0; q < S; ++q) acc[q] += x[u][q] * inv;
+        if (tail && seg_ok && (ROWS_OK || (unsigned)u < n_left)) {
+            for (unsigned c = g + G * S; c < w; c += G) {
+                const int tt = c < d ? bi[c * ids_stride + ids_gi] : 0;
+                double f = __ldg(theta + tt) * cr[u * row_stride + c * nsb];
+                if (f < kEpsilon) f = 0.0;
+                const double wgt = f * inv;
+                if (tt == 0) acc0 += wgt;
+                else if (wgt != 0.0) red_add_f64(count + tt, wgt);
+            }
+        }
+    }
+}
+
+// One batch: P = 32 / G segments of n rows x (d + 1) columns; lane = g * P + gi owns columns g, g + G, ... of segment
+// gi: ids and theta are loaded once, the rows are walked U at a time (instruction-level parallelism across the
+// load -> product -> row sum -> reciprocal chain), the normalised weights are summed per lane and leave as ONE
+// reduction per transcript and segment.  The noise column's sum stays in the thread (count[0] is flushed per CTA).
 template <int G, int S, int U>
 __device__ __forceinline__ double process_batch(const double* __restrict__ bv, const int* __restrict__ bi, unsigned d,
                                                 unsigned n, unsigned nsb, bool same, const double* __restrict__ theta,
-                                                double theta0, double* count, unsigned lane) {
+                                                double* count, unsigned lane) {
     constexpr unsigned P = 32 / G;
     const unsigned gi = lane % P, g = lane / P;
     const bool seg_ok = gi < nsb;
+    const unsigned w = d + 1u;
     const unsigned ids_stride = same ? 1u : nsb, ids_gi = same ? 0u : gi;
     int t[S];
     double th[S], acc[S];
-#pragma unroll
-    for (int q = 0; q < S; ++q) {
-        const unsigned c = g + G * q;
-        t[q] = (seg_ok && c < d) ? bi[c * ids_stride + ids_gi] : 0;
-    }
-#pragma unroll
-    for (int q = 0; q < S; ++q) {
-        // columns beyond the degree (and idle segments) multiply by 0: their products vanish without a predicate
-        th[q] = (seg_ok && g + G * q < d) ? __ldg(theta + t[q]) : 0.0;
-        acc[q] = 0.0;
-    }
-    const double* ncp = bv + gi;               // [r][gi]
-    const double* con = bv + nsb * n + gi;     // [(r d + c)][gi]
-    const unsigned row_stride = d * nsb;
-    double acc0 = 0.0;
-    const bool has_tail = d > (unsigned)(G * S);  // only possible for G = 32 (d > 128)
     bool col_ok[S];
     unsigned coff[S];
 #pragma unroll
     for (int q = 0; q < S; ++q) {
-        col_ok[q] = seg_ok && g + G * q < d;
-        coff[q] = (g + G * q) * nsb;
+        const unsigned c = g + G * q;
+        col_ok[q] = seg_ok && c < w;
+        coff[q] = c * nsb;
+        t[q] = (seg_ok && c < d) ? bi[c * ids_stride + ids_gi] : 0;  // column d is the noise entry: transcript 0
     }
-
-    for (unsigned r = 0; r < n; r += U) {
-        double x[U][S], part[U], f0[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const unsigned rr = (r + u < n) ? r + u : r;  // a row past the end re-reads row r and is discarded below
-            const double* cr = con + (unsigned long long)rr * row_stride;
-#pragma unroll
-            for (int q = 0; q < S; ++q) {
-                double c = 0.0;  // idle lanes (column beyond the degree, segment beyond the batch) must not read: the
-                if (col_ok[q]) c = cr[coff[q]];  // bytes behind a batch are arbitrary (possibly NaN patterns)
-                x[u][q] = th[q] * c;
-                if (x[u][q] < kEpsilon) x[u][q] = 0.0;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (S == 4) part[u] = (x[u][0] + x[u][1]) + (x[u][2] + x[u][3]);
-            else part[u] = (x[u][0] + x[u][1]) + x[u][2];
-        }
-        if (has_tail && seg_ok) {
-            for (unsigned c = g + G * S; c < d; c += G) {
-                const double thc = __ldg(theta + bi[c * ids_stride + ids_gi]);
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (r + u < n) {
-                        double f = thc * con[(unsigned long long)(r + u) * row_stride + c * nsb];
-                        if (f < kEpsilon) f = 0.0;
-                        part[u] += f;
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            f0[u] = 0.0;
-            if (g == 0 && seg_ok && r + u < n) {
-                f0[u] = theta0 * ncp[(r + u) * nsb];
-                if (f0[u] < kEpsilon) f0[u] = 0.0;
-                part[u] += f0[u];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) part[u] = seg_sum<G>(part[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            double inv = part[u] >= kEpsilon ? 1.0 / part[u] : 0.0;
-            if (u > 0 && r + u >= n) inv = 0.0;
-            acc0 += f0[u] * inv;
-#pragma unroll
-            for (int q = 0; q < S; ++q) acc[q] += x[u][q] * inv;
-            if (has_tail && seg_ok && r + u < n) {
-                for (unsigned c = g + G * S; c < d; c += G) {
-                    const int tt = bi[c * ids_stride + ids_gi];
-                    double f = __ldg(theta + tt) * con[(unsigned long long)(r + u) * row_stride + c * nsb];
-                    if (f < kEpsilon) f = 0.0;
-                    const double w = f * inv;
-                    if (w != 0.0) red_add_f64(count + tt, w);
-                }
-            }
-        }
+    for (int q = 0; q < S; ++q) {
+        th[q] = col_ok[q] ? __ldg(theta + t[q]) : 0.0;
+        acc[q] = 0.0;
     }
+    const double* con = bv + gi;  // value (r, c) of this lane's segment at con[(r w + c) nsb]
+    const unsigned row_stride = w * nsb;
+    const bool tail = w > (unsigned)(G * S);  // only possible for G = 32
+    double acc0 = 0.0;
+    unsigned r = 0;
+    for (; r + U <= n; r += U)
+        batch_rows<G, S, U, true>(con + (unsigned long long)r * row_stride, row_stride, U, th, col_ok, coff, acc, tail, g, w, nsb, d,
+                                  bi, ids_stride, ids_gi, seg_ok, theta, count, acc0);
+    if (U > 1 && r < n)
+        batch_rows<G, S, U, false>(con + (unsigned long long)r * row_stride, row_stride, n - r, th, col_ok, coff, acc, tail, g, w, nsb,
+                                   d, bi, ids_stride, ids_gi, seg_ok, theta, count, acc0);
     if (same && P > 1) {  // every segment of the batch adds to the same transcripts: fold them first
 #pragma unroll
         for (int q = 0; q < S; ++q) {
@@ -505,23 +524,29 @@ __device__ __forceinline__ double process_batch(const double* __restrict__ bv, c
         }
     }
 #pragma unroll
-    for (int q = 0; q < S; ++q)
-        if (acc[q] != 0.0) red_add_f64(count + t[q], acc[q]);
+    for (int q = 0; q < S; ++q) {
+        if (t[q] == 0) acc0 += acc[q];  // noise column (or an idle slot, whose sum is 0)
+        else if (acc[q] != 0.0) red_add_f64(count + t[q], acc[q]);
+    }
     return acc0;
 }
 
-template <int T, int U>
-__global__ void __launch_bounds__(T, 1) estep_class_kernel(const ClassArgs a) {
+// W consumer warps + 1 producer warp per CTA (one CTA per SM).  The producer's lane 0 keeps the 3-stage ring full:
+// it waits on a stage's "empty" barrier (one arrival per consumer warp) and issues the next tile's bulk copies on its
+// "full" barrier.  Consumers wait for "full", take the batches whose global index is congruent to their warp index
+// (batches of a tile have similar shape, so the static assignment is balanced and costs no atomics), arrive on "empty".
+template <int W, int U>
+__global__ void __launch_bounds__((W + 1) * 32, 1) estep_class_kernel(const ClassArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    ClassSmem<T>& sm = *reinterpret_cast<ClassSmem<T>*>(smem_raw);
+    ClassSmem<W>& sm = *reinterpret_cast<ClassSmem<W>*>(smem_raw);
     if (*a.done_flag) return;
-    constexpr unsigned kWarps = T / 32;
-    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    unsigned long long t_start = 0;
     if (tid == 0) {
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&sm.full_bar[s], 1);
-            sm.next_batch[s] = 0;
-            sm.warps_done[s] = 0;
+            mbar_init(&sm.empty_bar[s], W);
         }
         fence_barrier_init();
     }
@@ -529,78 +554,87 @@ __global__ void __launch_bounds__(T, 1) estep_class_kernel(const ClassArgs a) {
     // tiles strided by the grid: neighbouring tiles hold batches of similar shape (the stream is sorted by degree), so
     // every CTA sees the same mix
     const unsigned k_first = blockIdx.x, k_step = gridDim.x, k_end = a.n_tiles;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            const unsigned long long k = (unsigned long long)k_first + (unsigned long long)s * k_step;
-            if (k < k_end) issue_class_tile(a, (unsigned)k, sm.stage[s], &sm.full_bar[s], sm.sd[s]);
-        }
-    }
-    const double theta0 = __ldg(a.theta);
     double acc0 = 0.0;
-    unsigned it = 0;
-    for (unsigned long long k = k_first; k < k_end; k += k_step, ++it) {
-        const int s = it % kStages;
-        const unsigned parity = (it / kStages) & 1u;
-        mbar_wait(&sm.full_bar[s], parity);
-        const unsigned char* st = sm.stage[s];
-        const StageDesc sd = sm.sd[s];
-        const double* s_val = reinterpret_cast<const double*>(st);
-        const int* s_ids = reinterpret_cast<const int*>(st + sd.o_ids);
-        const BatchDesc* s_desc = reinterpret_cast<const BatchDesc*>(st + sd.o_desc);
-        for (;;) {
-            unsigned b = 0;
-            if (lane == 0) b = atomicAdd(&sm.next_batch[s], 1u);
-            b = __shfl_sync(0xffffffffu, b, 0);
-            if (b >= sd.n_batches) break;
-            const BatchDesc bd = s_desc[b];
-            const unsigned d = (unsigned)(bd.w0 >> 48), n = (unsigned)(bd.w1 >> 40) & 255u, nsb = (unsigned)(bd.w1 >> 48) & 255u;
-            const unsigned cfg = (unsigned)(bd.w1 >> 56) & 15u;
-            const bool same = (bd.w1 >> 60) & 1ull;
-            const double* bv = s_val + ((bd.w0 & kOff48) - sd.val_base);
-            const int* bi = s_ids + ((bd.w1 & kOff40) - sd.id_base);
-            switch (cfg) {
-                case 0: acc0 += process_batch<1, 3, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
-                case 1: acc0 += process_batch<1, 4, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
-                case 2: acc0 += process_batch<2, 3, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
-                case 3: acc0 += process_batch<2, 4, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
-                case 4: acc0 += process_batch<4, 3, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
-                case 5: acc0 += process_batch<4, 4, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
-                case 6: acc0 += process_batch<8, 3, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
-                case 7: acc0 += process_batch<8, 4, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
-                case 8: acc0 += process_batch<16, 3, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
-                case 9: acc0 += process_batch<16, 4, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
-                case 10: acc0 += process_batch<32, 3, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
-                default: acc0 += process_batch<32, 4, U>(bv, bi, d, n, nsb, same, a.theta, theta0, a.count, lane); break;
+    if (warp == W) {
+        if (lane == 0) {
+            unsigned it = 0;
+            for (unsigned long long k = k_first; k < k_end; k += k_step, ++it) {
+                const int s = it % kStages;
+                if (it >= (unsigned)kStages) {
+                    mbar_wait(&sm.empty_bar[s], ((it / kStages) - 1u) & 1u);
+                    fence_proxy_async();  // the consumers' generic-proxy reads precede the async-proxy refill
+                }
+                issue_class_tile(a, (unsigned)k, sm.stage[s], &sm.full_bar[s], sm.sd[s], W);
             }
         }
-        // this warp is done reading stage s: order its shared-memory reads before the last warp's refill
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            const unsigned old = atomicAdd(&sm.warps_done[s], 1u);
-            if (old == kWarps - 1) {
-                __threadfence_block();
-                sm.warps_done[s] = 0;
-                sm.next_batch[s] = 0;
-                const unsigned long long kn = k + (unsigned long long)kStages * k_step;
-                if (kn < k_end) {
-                    fence_proxy_async();
-                    issue_class_tile(a, (unsigned)kn, sm.stage[s], &sm.full_bar[s], sm.sd[s]);
+    } else {
+        unsigned it = 0;
+        for (unsigned long long k = k_first; k < k_end; k += k_step, ++it) {
+            const int s = it % kStages;
+            mbar_wait(&sm.full_bar[s], (it / kStages) & 1u);
+            const unsigned char* st = sm.stage[s];
+            const StageDesc sd = sm.sd[s];
+            const double* s_val = reinterpret_cast<const double*>(st);
+            const int* s_ids = reinterpret_cast<const int*>(st + sd.o_ids);
+            const BatchDesc* s_desc = reinterpret_cast<const BatchDesc*>(st + sd.o_desc);
+            for (unsigned b = (warp + W - sd.first_batch_mod) % W; b < sd.n_batches; b += W) {
+                const BatchDesc bd = s_desc[b];
+                const unsigned d = (unsigned)(bd.w0 >> 48), n = (unsigned)(bd.w1 >> 40) & 255u, nsb = (unsigned)(bd.w1 >> 48) & 255u;
+                const unsigned cfg = (unsigned)(bd.w1 >> 56) & 15u;
+                const bool same = (bd.w1 >> 60) & 1ull;
+                const double* bv = s_val + ((bd.w0 & kOff48) - sd.val_base);
+                const int* bi = s_ids + ((bd.w1 & kOff40) - sd.id_base);
+#ifdef RB_CLASS_DEBUG
+                {
+                    const unsigned long long vo = (bd.w0 & kOff48) - sd.val_base;
+                    const unsigned long long nv = (unsigned long long)nsb * n * (d + 1);
+                    const bool bad = cfg != cfg_of_deg(d) || nsb == 0 || nsb > 32u / group_of_deg(d) || n == 0 ||
+                                     (vo + nv) * 8ull > sd.o_ids || sd.n_batches > 4096;
+                    bool nan = false;
+                    if (!bad)
+                        for (unsigned long long i = lane; i < nv; i += 32) nan = nan || (bv[i] != bv[i]) || bv[i] < 0.0 || bv[i] > 1.0;
+                    if ((bad || __any_sync(0xffffffffu, nan)) && lane == 0 && atomicCAS(&g_dbg_flag, 0, 1) == 0)
+                        printf("CLASSDBG cta %u warp %u it %u s %d k %llu b %u/%u bad %d | d %u n %u nsb %u cfg %u vo %llu nv %llu o_ids %u o_desc %u "
+                               "val_base %llu id_base %llu fbm %u | w0 %llx w1 %llx\n",
+                               blockIdx.x, warp, it, s, k, b, sd.n_batches, (int)bad, d, n, nsb, cfg, vo, nv, sd.o_ids, sd.o_desc, sd.val_base,
+                               sd.id_base, sd.first_batch_mod, bd.w0, bd.w1);
+                }
+#endif
+                switch (cfg) {
+                    case 0: acc0 += process_batch<1, 3, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
+                    case 1: acc0 += process_batch<1, 4, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
+                    case 2: acc0 += process_batch<2, 3, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
+                    case 3: acc0 += process_batch<2, 4, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
+                    case 4: acc0 += process_batch<4, 3, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
+                    case 5: acc0 += process_batch<4, 4, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
+                    case 6: acc0 += process_batch<8, 3, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
+                    case 7: acc0 += process_batch<8, 4, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
+                    case 8: acc0 += process_batch<16, 3, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
+                    case 9: acc0 += process_batch<16, 4, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
+                    case 10: acc0 += process_batch<32, 3, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
+                    default: acc0 += process_batch<32, 4, U>(bv, bi, d, n, nsb, same, a.theta, a.count, lane); break;
                 }
             }
+            __syncwarp();  // every lane's reads of the stage are done before lane 0 releases it
+            if (lane == 0) mbar_arrive(&sm.empty_bar[s]);
         }
     }
-    __syncthreads();
     // count[0] partials: warp shuffle -> shared -> one reduction per CTA
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-    if (lane == 0) sm.red[tid >> 5] = acc0;
+    if (lane == 0) sm.red[warp] = acc0;
     __syncthreads();
-    if (tid < 32) {
-        double v = lane < kWarps ? sm.red[lane] : 0.0;
+    if (warp == 0) {
+        double v = 0.0;
+        for (unsigned i = lane; i < (unsigned)W; i += 32) v += sm.red[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0 && v != 0.0) red_add_f64(a.count, v);
+        if (lane == 0) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+            a.cta_ns[blockIdx.x] = t_end - t_start;
+        }
     }
 }
 
@@ -701,7 +735,7 @@ struct PhaseTimer {  // RSEM_B200_CLASS_TIMING=1: wall-clock per build phase on 
 void class_free(rsem_b200_ctx* ctx) {
     ClassLayout& L = ctx->cls;
     cudaFree(L.vals); cudaFree(L.ids); cudaFree(L.desc); cudaFree(L.tile); cudaFree(L.batch_first);
-    cudaFree(L.fseg_first); cudaFree(L.rows); cudaFree(L.long_rows);
+    cudaFree(L.fseg_first); cudaFree(L.rows); cudaFree(L.long_rows); cudaFree(L.cta_ns);
     L = ClassLayout{};
 }
 
@@ -911,8 +945,8 @@ int class_build(rsem_b200_ctx* ctx) {
     L.R = R;
     // measured on C3 (ms per round): 512 threads x 128 registers, two rows in flight per lane: 2.27; 1024 x 64, one row: 2.49
     L.threads = 512;
-    if (const char* e = getenv("RSEM_B200_CLASS_THREADS")) {  // tuning knob
-        if (atoi(e) == 1024) L.threads = 1024;
+    if (const char* e = getenv("RSEM_B200_CLASS_THREADS")) {  // tuning knob: 512, 513 (3 rows in flight), 544, 640, 768, 1024
+        L.threads = atoi(e);
     }
     L.built = true;
     L.vals_epoch = 0;
@@ -948,19 +982,29 @@ int class_launch_estep(rsem_b200_ctx* ctx) {
         a.theta = ctx->theta;
         a.count = ctx->count;
         a.done_flag = ctx->done_flag;
-        const int threads = L.threads;
+        if (!L.cta_ns) {
+            RB_CUDA(cudaMalloc(&L.cta_ns, (size_t)ctx->sm_count * sizeof(unsigned long long)));
+        }
+        a.cta_ns = reinterpret_cast<unsigned long long*>(L.cta_ns);
         unsigned grid = (unsigned)ctx->sm_count;
         if (grid > L.n_tiles) grid = L.n_tiles;
-        if (threads == 512) {
-            auto kern = estep_class_kernel<512, 2>;
-            const size_t smem = sizeof(ClassSmem<512>);
-            RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, 512, smem, ctx->stream>>>(a);
-        } else {
-            auto kern = estep_class_kernel<1024, 1>;
-            const size_t smem = sizeof(ClassSmem<1024>);
-            RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, 1024, smem, ctx->stream>>>(a);
+        L.last_grid = grid;
+        // consumer warps x rows in flight per lane; measured on C3 in profiles/README.md
+        switch (L.threads) {
+#define RB_CLASS_LAUNCH(W, U)                                                                                   \
+    {                                                                                                           \
+        auto kern = estep_class_kernel<W, U>;                                                                   \
+        const size_t smem = sizeof(ClassSmem<W>);                                                               \
+        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        kern<<<grid, (W + 1) * 32, smem, ctx->stream>>>(a);                                                     \
+    }
+            case 1024: RB_CLASS_LAUNCH(31, 1) break;
+            case 768: RB_CLASS_LAUNCH(23, 2) break;
+            case 640: RB_CLASS_LAUNCH(19, 2) break;
+            case 544: RB_CLASS_LAUNCH(16, 2) break;
+            case 513: RB_CLASS_LAUNCH(15, 3) break;
+            default: RB_CLASS_LAUNCH(15, 2) break;
+#undef RB_CLASS_LAUNCH
         }
         RB_CUDA(cudaGetLastError());
         ctx->launches++;

@@ -122,6 +122,8 @@ struct ClassLayout {
     uint32_t* fseg_first = nullptr;   // first sorted row position of every segment (final order)
     uint32_t* rows = nullptr;         // sorted position -> original row
     uint32_t* long_rows = nullptr;    // original rows with more than kLongDeg hits
+    uint64_t* cta_ns = nullptr;       // per-CTA busy time (ns) of the latest class-kernel launch
+    uint32_t last_grid = 0;
 };
 
 }  // namespace rsem_b200
@@ -192,6 +194,12 @@ struct rsem_b200_ctx {
     // multi-GPU
     void* comm = nullptr;
     int n_ranks = 1, rank = 0;
+
+    // RSEM_B200_PHASE_TIMING=1: device time per kernel of the model rounds (K1, K2 with posteriors, K3), printed at destroy
+    bool phase_timing = false;
+    cudaEvent_t ph_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double ph_ms[3] = {0, 0, 0};
+    uint64_t ph_n[3] = {0, 0, 0};
 
     // profiling of K2
     bool profiling = false;

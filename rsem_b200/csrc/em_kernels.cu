@@ -927,6 +927,9 @@ __global__ void __cluster_dims__(kThetaCluster, 1, 1) __launch_bounds__(1024)
     __shared__ double cl_b[kThetaCluster];       // rank 0 receives the partial statistics
     __shared__ long long cl_t[kThetaCluster];
     if (*done_flag) return;  // same value in every CTA of the cluster
+    // distributed shared memory may only be written once the target CTA has started executing (racecheck: "block that
+    // might not have entered yet"): every CTA of the cluster passes this barrier before the first remote store
+    cluster.sync();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const unsigned rank = cluster.block_rank();
     const int first = (int)rank * (int)blockDim.x + tid, step = kThetaCluster * (int)blockDim.x;

@@ -137,15 +137,22 @@ int main(int argc, char* argv[]) {
     std::vector<double> alpha(M + 1, pseudoC);
     if (has_prior) {  // load_prior_info (Gibbs.cpp:171-194)
         alpha.assign(M + 1, 0.0);
-        FILE* fi = fopen(fprior.c_str(), "r");
-        if (!fi) die("Cannot open " + fprior + "!");
-        char line[4096];
+        // one prior per transcript and line, anything after the number is a comment (Gibbs.cpp:178-184 uses getline:
+        // no limit on the line length)
+        std::vector<char> buf = slurp(fprior);
+        buf.push_back('\0');
+        const char* q = buf.data();
+        const char* const end = q + buf.size() - 1;
         for (int i = 1; i <= M; ++i) {
-            double prior = 0.0;
-            if (fgets(line, sizeof line, fi)) sscanf(line, "%lf", &prior);
+            if (q >= end) die("The prior file " + fprior + " has fewer lines than transcripts!");
+            const char* eol = static_cast<const char*>(memchr(q, '\n', (size_t)(end - q)));
+            if (!eol) eol = end;
+            char* after = nullptr;
+            const double prior = strtod(q, &after);
+            if (after == q || after > eol) die("Cannot read the prior of transcript " + std::to_string(i) + " from " + fprior + "!");
             if (init_counts[i] == 0) alpha[i] = prior;
+            q = eol < end ? eol + 1 : end;
         }
-        fclose(fi);
         totc = 1;
         for (int i = 1; i <= M; ++i)
             if (init_counts[i] == 0) totc += alpha[i];

@@ -216,6 +216,27 @@ def test_class_layout_matches_oracle(ctx, oracle, case, monkeypatch):
     ctx.set_estep_variant(0)
 
 
+@pytest.mark.parametrize("threads", [512, 640, 1024])
+def test_class_layout_ring_reuse(ctx, oracle, threads, monkeypatch):
+    """enough tiles (~1600) that every persistent CTA refills its shared-memory stages several times: the producer /
+    consumer hand-over of the ring is exercised, not only its first fill"""
+    monkeypatch.setenv("RSEM_B200_CLASS_THREADS", str(threads))
+    N, M = 500_000, 20_000
+    row_ptr, sid, conprb, ncpv = _class_matrix(N, M, 20, seed=11, dup=10)
+    n0 = N / 20
+    theta0 = synth.init_theta(M, n0, N + n0)
+    theta_ref, _, _ = oracle.em_rounds(row_ptr, sid, conprb, ncpv, theta0, n0, 1, 3, 20, 10000, n_threads=16)
+    ctx.set_estep_variant(5)
+    ctx.upload_hits(row_ptr, sid, M)
+    ctx.upload_conprb(conprb, ncpv)
+    for _ in range(5):  # repeated: a hand-over race would be timing dependent
+        ctx.set_theta(theta0)
+        ctx.em_rounds(1, 3, 20, 10000, n0)
+        _check_theta(ctx.get_theta(), theta_ref)
+    assert ctx.class_layout_info()["tiles"] > 3 * 148
+    ctx.set_estep_variant(0)
+
+
 def test_class_layout_c5_shape_one_million_reads(ctx, oracle):
     """BASELINE configs[4] shape at a size the oracle finishes in seconds: Zipf(1.1) degrees capped at 200, 1 M reads,
     every kernel variant against the oracle"""
@@ -277,6 +298,7 @@ def test_full_size_properties(ctx):
     n0 = N / 20
     theta0 = synth.init_theta(M, n0, N + n0)
     ctx.set_estep_variant(0)
+    torch.cuda.synchronize()  # the generator's stream is not the context's
     ctx.adopt_device_matrix(N, H, M, row_ptr.data_ptr(), sid.data_ptr(), conprb.data_ptr(), ncpv.data_ptr())
     ctx.set_theta(theta0)
     stats, _ = ctx.em_rounds(1, 3, 20, 10000, n0)
