@@ -56,7 +56,7 @@ def build_host(force: bool = False):
         if force or _newer(out, deps + [os.path.join(ROOT, "rsem_b200", "librsem_b200.so")]):
             _run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", out, m, *shared,
                   "-L", os.path.join(ROOT, "rsem_b200"), "-lrsem_b200", "-Wl,-rpath,$ORIGIN/../rsem_b200",
-                  "-static-libstdc++", "-static-libgcc"])
+                  "-static-libstdc++", "-static-libgcc", "-lz"])
 
 
 def build_tools(force: bool = False):

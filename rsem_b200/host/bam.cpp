@@ -1,0 +1,516 @@
+// SAM / BAM input and BAM output for rsem-run-em -b (posterior-annotated transcript BAM).
+//
+// What it replaces: the reference re-reads its input alignment file with htslib and writes every record back with
+// MAPQ and a ZW:f tag set from the posterior of the alignment (/root/reference/BamWriter.h:39-48, 82-146;
+// sam_utils.h:72-76), in input order.  The reference vendors htslib for this; here the two container formats are
+// implemented directly on zlib (SAM v1 / BAM as in the SAM specification, BGZF = concatenated gzip members with a
+// "BC" extra field), because only sequential record read / rewrite is needed:
+//   * AlnReader: SAM text (plain or gzip) or BAM; yields BAM-encoded records (SAM lines are converted with the same
+//     field encodings htslib's sam_parse1 uses, e.g. the smallest integer type for i-tags);
+//   * BamWriter: BGZF blocks of <= 0xff00 bytes, compressed by a pool of host threads (-p), written in order, EOF marker.
+// CRAM is not supported (the run stops with a clear message).
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <thread>
+
+#include "host.hpp"
+
+namespace host {
+
+namespace {
+
+inline uint32_t rd_u32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint16_t rd_u16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline void wr_u32(uint8_t* p, uint32_t v) { p[0] = v & 255; p[1] = (v >> 8) & 255; p[2] = (v >> 16) & 255; p[3] = (v >> 24) & 255; }
+inline void wr_u16(uint8_t* p, uint16_t v) { p[0] = v & 255; p[1] = (v >> 8) & 255; }
+template <class T>
+inline void put(std::vector<uint8_t>& v, T x) {
+    uint8_t b[sizeof(T)];
+    memcpy(b, &x, sizeof(T));  // little-endian host (x86-64 / aarch64)
+    v.insert(v.end(), b, b + sizeof(T));
+}
+
+// SAM spec 5.3: the UCSC binning scheme
+int reg2bin(int64_t beg, int64_t end) {
+    --end;
+    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+
+int aux_type_size(char x) {  // sam_utils.h:24-30
+    if (x == 'C' || x == 'c' || x == 'A') return 1;
+    if (x == 'S' || x == 's') return 2;
+    if (x == 'I' || x == 'i' || x == 'f') return 4;
+    if (x == 'd') return 8;
+    return 0;
+}
+
+}  // namespace
+
+// ---- raw byte source: plain file or gzip / BGZF (zlib's gz* layer reads concatenated members transparently) ---------
+struct AlnReader::Source {
+    gzFile gz = nullptr;
+    std::vector<uint8_t> buf;
+    size_t at = 0, end = 0;
+    bool eof = false;
+    bool fill() {
+        if (eof) return false;
+        if (at < end) memmove(buf.data(), buf.data() + at, end - at);
+        end -= at;
+        at = 0;
+        const int n = gzread(gz, buf.data() + end, (unsigned)(buf.size() - end));
+        if (n < 0) die("Error while reading the alignment file (corrupt gzip / BGZF stream)!");
+        if (n == 0) { eof = true; return false; }
+        end += (size_t)n;
+        return true;
+    }
+    bool read(void* dst, size_t n) {  // exactly n bytes, false at a clean EOF before the first byte
+        uint8_t* d = static_cast<uint8_t*>(dst);
+        size_t got = 0;
+        while (got < n) {
+            if (at == end && !fill()) {
+                if (got == 0) return false;
+                die("Truncated BAM file!");
+            }
+            const size_t k = std::min(n - got, end - at);
+            memcpy(d + got, buf.data() + at, k);
+            at += k;
+            got += k;
+        }
+        return true;
+    }
+    bool line(std::string& out) {  // one text line without the terminator
+        out.clear();
+        for (;;) {
+            if (at == end && !fill()) return !out.empty();
+            const uint8_t* p = static_cast<const uint8_t*>(memchr(buf.data() + at, '\n', end - at));
+            if (p) {
+                out.append(reinterpret_cast<const char*>(buf.data() + at), (size_t)(p - (buf.data() + at)));
+                at = (size_t)(p - buf.data()) + 1;
+                if (!out.empty() && out.back() == '\r') out.pop_back();
+                return true;
+            }
+            out.append(reinterpret_cast<const char*>(buf.data() + at), end - at);
+            at = end;
+        }
+    }
+};
+
+AlnReader::AlnReader(const std::string& path) : src_(new Source) {
+    FILE* probe = fopen(path.c_str(), "rb");
+    if (!probe) die("Cannot open " + path + "! It may not exist.");
+    uint8_t magic[4] = {0, 0, 0, 0};
+    const size_t got = fread(magic, 1, 4, probe);
+    fclose(probe);
+    if (got >= 4 && !memcmp(magic, "CRAM", 4)) die("rsem-run-em (B200): CRAM input for -b is not supported; convert it to BAM (convert-sam-for-rsem).");
+    src_->gz = gzopen(path.c_str(), "rb");
+    if (!src_->gz) die("Cannot open " + path + "! It may not exist.");
+    gzbuffer(src_->gz, 1 << 20);
+    src_->buf.resize(4 << 20);
+    // BAM = gzip stream whose payload starts with "BAM\1"; anything else is SAM text
+    uint8_t m4[4];
+    src_->fill();
+    is_bam_ = src_->end - src_->at >= 4 && !memcmp(src_->buf.data() + src_->at, "BAM\1", 4);
+    if (is_bam_) {
+        src_->read(m4, 4);
+        uint8_t b4[4];
+        if (!src_->read(b4, 4)) die("Truncated BAM header!");
+        const uint32_t l_text = rd_u32(b4);
+        text_.resize(l_text);
+        if (l_text && !src_->read(&text_[0], l_text)) die("Truncated BAM header!");
+        while (!text_.empty() && text_.back() == '\0') text_.pop_back();
+        if (!src_->read(b4, 4)) die("Truncated BAM header!");
+        const uint32_t n_ref = rd_u32(b4);
+        for (uint32_t i = 0; i < n_ref; ++i) {
+            if (!src_->read(b4, 4)) die("Truncated BAM header!");
+            const uint32_t l_name = rd_u32(b4);
+            std::string name(l_name, '\0');
+            if (!src_->read(&name[0], l_name)) die("Truncated BAM header!");
+            while (!name.empty() && name.back() == '\0') name.pop_back();
+            if (!src_->read(b4, 4)) die("Truncated BAM header!");
+            ref_names_.push_back(name);
+            ref_lens_.push_back(rd_u32(b4));
+        }
+    } else {
+        // header lines up to the first alignment line (kept as the pending line)
+        std::string ln;
+        while (src_->line(ln)) {
+            if (ln.empty()) continue;
+            if (ln[0] != '@') { pending_ = ln; have_pending_ = true; break; }
+            text_ += ln;
+            text_ += '\n';
+            if (ln.compare(0, 3, "@SQ") == 0) {
+                std::string name;
+                uint32_t len = 0;
+                size_t fr = 4;
+                while (fr < ln.size()) {
+                    size_t to = ln.find('\t', fr);
+                    if (to == std::string::npos) to = ln.size();
+                    if (ln.compare(fr, 3, "SN:") == 0) name = ln.substr(fr + 3, to - fr - 3);
+                    else if (ln.compare(fr, 3, "LN:") == 0) len = (uint32_t)strtoul(ln.c_str() + fr + 3, nullptr, 10);
+                    fr = to + 1;
+                }
+                ref_names_.push_back(name);
+                ref_lens_.push_back(len);
+            }
+        }
+    }
+    for (size_t i = 0; i < ref_names_.size(); ++i) ref_index_[ref_names_[i]] = (int)i;
+}
+
+AlnReader::~AlnReader() {
+    if (src_->gz) gzclose(src_->gz);
+    delete src_;
+}
+
+bool AlnReader::next(BamRecord& rec) {
+    if (is_bam_) {
+        uint8_t b4[4];
+        if (!src_->read(b4, 4)) return false;
+        const uint32_t block = rd_u32(b4);
+        if (block < 32) die("Corrupt BAM record!");
+        rec.data.resize(block);
+        if (!src_->read(rec.data.data(), block)) die("Truncated BAM file!");
+        return true;
+    }
+    std::string ln;
+    if (have_pending_) { ln.swap(pending_); have_pending_ = false; }
+    else {
+        do {
+            if (!src_->line(ln)) return false;
+        } while (ln.empty());
+    }
+    parse_sam_line(ln, rec);
+    return true;
+}
+
+// SAM text -> BAM record (SAM spec section 4.2; field encodings as htslib's sam_parse1 chooses them)
+void AlnReader::parse_sam_line(const std::string& ln, BamRecord& rec) const {
+    std::vector<std::pair<size_t, size_t>> f;  // [begin, end) of every tab-separated field
+    for (size_t fr = 0; fr <= ln.size();) {
+        size_t to = ln.find('\t', fr);
+        if (to == std::string::npos) to = ln.size();
+        f.emplace_back(fr, to);
+        fr = to + 1;
+    }
+    if (f.size() < 11) die("Malformed SAM line (fewer than 11 fields): " + ln.substr(0, 80));
+    auto S = [&](int i) { return ln.substr(f[i].first, f[i].second - f[i].first); };
+    const std::string qname = S(0), rname = S(2), cigar = S(5), rnext = S(6), seq = S(9), qual = S(10);
+    const int flag = atoi(S(1).c_str());
+    const int64_t pos = atoll(S(3).c_str()) - 1, pnext = atoll(S(7).c_str()) - 1, tlen = atoll(S(8).c_str());
+    const int mapq = atoi(S(4).c_str());
+    auto ref_id = [&](const std::string& n) -> int {
+        if (n == "*") return -1;
+        auto it = ref_index_.find(n);
+        if (it == ref_index_.end()) die("SAM line refers to a reference sequence that is not in the header: " + n);
+        return it->second;
+    };
+    const int tid = ref_id(rname);
+    const int mtid = rnext == "=" ? tid : ref_id(rnext);
+    // CIGAR
+    std::vector<uint32_t> cig;
+    int64_t ref_len = 0;
+    if (cigar != "*") {
+        static const char* OPS = "MIDNSHP=X";
+        const char* p = cigar.c_str();
+        while (*p) {
+            char* q;
+            const unsigned long n = strtoul(p, &q, 10);
+            const char* o = strchr(OPS, *q);
+            if (q == p || !*q || !o) die("Malformed CIGAR string: " + cigar);
+            const uint32_t op = (uint32_t)(o - OPS);
+            cig.push_back((uint32_t)(n << 4) | op);
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_len += (int64_t)n;
+            p = q + 1;
+        }
+    }
+    const int l_seq = seq == "*" ? 0 : (int)seq.size();
+    std::vector<uint8_t>& d = rec.data;
+    d.clear();
+    d.reserve(32 + qname.size() + 1 + cig.size() * 4 + (l_seq + 1) / 2 + l_seq + 64);
+    const int64_t end = (flag & 4) || cig.empty() || ref_len == 0 ? pos + 1 : pos + ref_len;
+    put<int32_t>(d, tid);
+    put<int32_t>(d, (int32_t)pos);
+    // an unplaced record (pos = -1) gets bin 4680 = reg2bin(-1, 0), as htslib computes it
+    put<uint32_t>(d, ((uint32_t)reg2bin(pos, end) << 16) | ((uint32_t)(mapq & 255) << 8) | (uint32_t)(qname.size() + 1));
+    put<uint32_t>(d, ((uint32_t)flag << 16) | (uint32_t)cig.size());
+    put<int32_t>(d, l_seq);
+    put<int32_t>(d, mtid);
+    put<int32_t>(d, (int32_t)pnext);
+    put<int32_t>(d, (int32_t)tlen);
+    d.insert(d.end(), qname.begin(), qname.end());
+    d.push_back(0);
+    for (uint32_t c : cig) put<uint32_t>(d, c);
+    static uint8_t nt16[256];
+    static bool nt_init = false;
+    if (!nt_init) {
+        memset(nt16, 15, sizeof nt16);
+        const char* code = "=ACMGRSVTWYHKDBN";
+        for (int i = 0; i < 16; ++i) { nt16[(uint8_t)code[i]] = (uint8_t)i; nt16[(uint8_t)tolower(code[i])] = (uint8_t)i; }
+        nt_init = true;
+    }
+    for (int i = 0; i < l_seq; i += 2) {
+        const uint8_t hi = nt16[(uint8_t)seq[i]], lo = i + 1 < l_seq ? nt16[(uint8_t)seq[i + 1]] : 0;
+        d.push_back((uint8_t)(hi << 4 | lo));
+    }
+    if (qual == "*") d.insert(d.end(), (size_t)l_seq, 0xff);
+    else {
+        if ((int)qual.size() != l_seq) die("SAM line with SEQ and QUAL of different lengths: " + qname);
+        for (int i = 0; i < l_seq; ++i) d.push_back((uint8_t)(qual[i] - 33));
+    }
+    // optional fields
+    for (size_t k = 11; k < f.size(); ++k) {
+        const size_t a = f[k].first, b = f[k].second;
+        if (b - a < 5 || ln[a + 2] != ':' || ln[a + 4] != ':') die("Malformed optional SAM field in the line of " + qname);
+        const char type = ln[a + 3];
+        const std::string val = ln.substr(a + 5, b - a - 5);
+        d.push_back((uint8_t)ln[a]);
+        d.push_back((uint8_t)ln[a + 1]);
+        if (type == 'A') { d.push_back('A'); d.push_back((uint8_t)(val.empty() ? ' ' : val[0])); }
+        else if (type == 'i') {
+            const long long x = atoll(val.c_str());
+            if (x < 0) {
+                if (x >= -128) { d.push_back('c'); put<int8_t>(d, (int8_t)x); }
+                else if (x >= -32768) { d.push_back('s'); put<int16_t>(d, (int16_t)x); }
+                else { d.push_back('i'); put<int32_t>(d, (int32_t)x); }
+            } else {
+                if (x <= 255) { d.push_back('C'); put<uint8_t>(d, (uint8_t)x); }
+                else if (x <= 65535) { d.push_back('S'); put<uint16_t>(d, (uint16_t)x); }
+                else { d.push_back('I'); put<uint32_t>(d, (uint32_t)x); }
+            }
+        } else if (type == 'f') { d.push_back('f'); put<float>(d, (float)atof(val.c_str())); }
+        else if (type == 'd') { d.push_back('d'); put<double>(d, atof(val.c_str())); }
+        else if (type == 'Z' || type == 'H') {
+            d.push_back((uint8_t)type);
+            d.insert(d.end(), val.begin(), val.end());
+            d.push_back(0);
+        } else if (type == 'B') {
+            if (val.empty()) die("Malformed B-type optional field in the line of " + qname);
+            const char sub = val[0];
+            std::vector<std::string> items;
+            for (size_t fr = 1; fr < val.size();) {
+                if (val[fr] == ',') ++fr;
+                size_t to = val.find(',', fr);
+                if (to == std::string::npos) to = val.size();
+                if (to > fr) items.push_back(val.substr(fr, to - fr));
+                fr = to;
+            }
+            d.push_back('B');
+            d.push_back((uint8_t)sub);
+            put<uint32_t>(d, (uint32_t)items.size());
+            for (const std::string& it : items) {
+                switch (sub) {
+                    case 'c': put<int8_t>(d, (int8_t)atoi(it.c_str())); break;
+                    case 'C': put<uint8_t>(d, (uint8_t)atoi(it.c_str())); break;
+                    case 's': put<int16_t>(d, (int16_t)atoi(it.c_str())); break;
+                    case 'S': put<uint16_t>(d, (uint16_t)atoi(it.c_str())); break;
+                    case 'i': put<int32_t>(d, (int32_t)atoll(it.c_str())); break;
+                    case 'I': put<uint32_t>(d, (uint32_t)atoll(it.c_str())); break;
+                    case 'f': put<float>(d, (float)atof(it.c_str())); break;
+                    default: die("Unknown B-array subtype in the line of " + qname);
+                }
+            }
+        } else die("Unknown optional field type in the line of " + qname);
+    }
+}
+
+// ---- BamRecord helpers ------------------------------------------------------------------------------------------------
+uint16_t BamRecord::flag() const { return (uint16_t)(rd_u32(data.data() + 12) >> 16); }
+int32_t BamRecord::tid() const { return (int32_t)rd_u32(data.data()); }
+
+// MAPQ + ZW:f from the posterior (BamWriter.h:39-48, sam_utils.h:72-76)
+void BamRecord::set_alignment_weight(double prb) {
+    const double err = 1.0 - prb;
+    const uint8_t mapq = err <= 1e-10 ? 100 : (uint8_t)(-10 * std::log10(err) + .5);
+    data[9] = mapq;  // bin_mq_nl: byte 8 = l_read_name, byte 9 = MAPQ
+    const float val = (float)prb;
+    // walk the optional fields to find an existing ZW
+    const uint32_t l_name = data[8], n_cig = rd_u32(data.data() + 12) & 0xffff;
+    const int32_t l_seq = (int32_t)rd_u32(data.data() + 16);
+    size_t at = 32 + l_name + 4 * (size_t)n_cig + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+    while (at + 3 <= data.size()) {
+        const char t0 = (char)data[at], t1 = (char)data[at + 1], type = (char)data[at + 2];
+        size_t val_at = at + 3, len;
+        if (type == 'Z' || type == 'H') {
+            len = 0;
+            while (val_at + len < data.size() && data[val_at + len]) ++len;
+            ++len;
+        } else if (type == 'B') {
+            const int sz = aux_type_size((char)data[val_at]);
+            len = 5 + (size_t)sz * rd_u32(data.data() + val_at + 1);
+        } else {
+            len = (size_t)aux_type_size(type);
+            if (len == 0) die("Corrupt optional field in a BAM record!");
+        }
+        if (t0 == 'Z' && t1 == 'W') {
+            memcpy(&data[val_at], &val, 4);  // the reference overwrites 4 bytes whatever the stored type is
+            return;
+        }
+        at = val_at + len;
+    }
+    data.push_back('Z');
+    data.push_back('W');
+    data.push_back('f');
+    put<float>(data, val);
+}
+
+// ---- header text as the reference rewrites it (SamHeader.cpp:74-114 + insertPG, SamHeader.hpp:38-60) -------------------
+std::string rsem_bam_header_text(const std::string& in_text) {
+    std::string HD, SQ, RG, PG, CO, other;
+    std::vector<std::string> pids;
+    size_t fr = 0;
+    while (fr < in_text.size()) {
+        size_t to = in_text.find('\n', fr);
+        if (to == std::string::npos) to = in_text.size();
+        const std::string line = in_text.substr(fr, to - fr);
+        fr = to + 1;
+        if (line.empty() || line[0] != '@') continue;
+        const std::string tag = line.substr(1, 2);
+        if (tag == "HD") {
+            if (!HD.empty()) die("@HD tag can only present once!");
+            HD = line + "\n";
+        } else if (tag == "SQ") SQ += line + "\n";
+        else if (tag == "RG") RG += line + "\n";
+        else if (tag == "PG") {
+            std::string id;
+            for (size_t a = 4; a < line.size();) {
+                size_t b = line.find('\t', a);
+                if (b == std::string::npos) b = line.size();
+                if (line.compare(a, 3, "ID:") == 0) id = line.substr(a + 3, b - a - 3);
+                a = b + 1;
+            }
+            if (std::find(pids.begin(), pids.end(), id) != pids.end()) die("Program record identifier " + id + " is not unique!");
+            pids.push_back(id);
+            PG += line + "\n";
+        } else if (tag == "CO") CO += line + "\n";
+        else other += line;  // sic: the reference appends these lines without their newline (SamHeader.cpp:111)
+    }
+    if (std::find(pids.begin(), pids.end(), std::string("RSEM")) == pids.end()) PG += "@PG\tID:RSEM\n";
+    return HD + SQ + RG + PG + CO + other;
+}
+
+// ---- BGZF writer ----------------------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t kBgzfBlock = 0xff00;
+
+void bgzf_compress(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+    out.resize(18 + compressBound((uLong)n) + 8);
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("zlib: deflateInit2 failed");
+    zs.next_in = const_cast<Bytef*>(src);
+    zs.avail_in = (uInt)n;
+    zs.next_out = out.data() + 18;
+    zs.avail_out = (uInt)(out.size() - 18 - 8);
+    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) die("zlib: deflate failed");
+    const size_t clen = zs.total_out;
+    deflateEnd(&zs);
+    static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    memcpy(out.data(), hdr, 16);
+    wr_u16(out.data() + 16, (uint16_t)(18 + clen + 8 - 1));
+    wr_u32(out.data() + 18 + clen, (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, (uInt)n));
+    wr_u32(out.data() + 18 + clen + 4, (uint32_t)n);
+    out.resize(18 + clen + 8);
+}
+}  // namespace
+
+BamWriter::BamWriter(const std::string& path, const std::string& header_text, int threads) : threads_(std::max(1, threads)) {
+    fo_ = fopen(path.c_str(), "wb");
+    if (!fo_) die("Cannot open " + path + " for writing!");
+    // references come from the @SQ lines of the (rewritten) text, like sam_hdr_parse does for the reference
+    std::vector<std::pair<std::string, uint32_t>> refs;
+    size_t fr = 0;
+    while (fr < header_text.size()) {
+        size_t to = header_text.find('\n', fr);
+        if (to == std::string::npos) to = header_text.size();
+        if (header_text.compare(fr, 3, "@SQ") == 0) {
+            std::string name;
+            uint32_t len = 0;
+            for (size_t a = fr + 4; a < to;) {
+                size_t b = header_text.find('\t', a);
+                if (b == std::string::npos || b > to) b = to;
+                if (header_text.compare(a, 3, "SN:") == 0) name = header_text.substr(a + 3, b - a - 3);
+                else if (header_text.compare(a, 3, "LN:") == 0) len = (uint32_t)strtoul(header_text.c_str() + a + 3, nullptr, 10);
+                a = b + 1;
+            }
+            refs.emplace_back(name, len);
+        }
+        fr = to + 1;
+    }
+    std::vector<uint8_t> h;
+    h.insert(h.end(), {'B', 'A', 'M', 1});
+    put<uint32_t>(h, (uint32_t)header_text.size());
+    h.insert(h.end(), header_text.begin(), header_text.end());
+    put<uint32_t>(h, (uint32_t)refs.size());
+    for (auto& r : refs) {
+        put<uint32_t>(h, (uint32_t)r.first.size() + 1);
+        h.insert(h.end(), r.first.begin(), r.first.end());
+        h.push_back(0);
+        put<uint32_t>(h, r.second);
+    }
+    append(h.data(), h.size());
+    flush_pending(true);  // htslib also ends the header in its own block
+}
+
+void BamWriter::append(const uint8_t* p, size_t n) {
+    pending_.insert(pending_.end(), p, p + n);
+    if (pending_.size() >= kBgzfBlock * 64 * (size_t)threads_) flush_pending(false);
+}
+
+void BamWriter::write(const BamRecord& rec) {
+    uint8_t b4[4];
+    wr_u32(b4, (uint32_t)rec.data.size());
+    append(b4, 4);
+    append(rec.data.data(), rec.data.size());
+}
+
+// compress the pending bytes block by block on the worker threads, write the blocks in order
+void BamWriter::flush_pending(bool all) {
+    const size_t n_blocks = all ? (pending_.size() + kBgzfBlock - 1) / kBgzfBlock : pending_.size() / kBgzfBlock;
+    if (n_blocks == 0) return;
+    std::vector<std::vector<uint8_t>> out(n_blocks);
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n_blocks) break;
+            const size_t a = i * kBgzfBlock, b = std::min(pending_.size(), a + kBgzfBlock);
+            bgzf_compress(pending_.data() + a, b - a, out[i]);
+        }
+    };
+    const int nt = (int)std::min<size_t>((size_t)threads_, n_blocks);
+    if (nt <= 1) work();
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; ++t) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+    }
+    for (auto& o : out)
+        if (fwrite(o.data(), 1, o.size(), fo_) != o.size()) die("Error while writing the BAM file!");
+    const size_t used = std::min(pending_.size(), n_blocks * kBgzfBlock);
+    pending_.erase(pending_.begin(), pending_.begin() + (long)used);
+}
+
+void BamWriter::close() {
+    if (!fo_) return;
+    flush_pending(true);
+    static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (fwrite(eof, 1, 28, fo_) != 28) die("Error while writing the BAM file!");
+    if (fclose(fo_) != 0) die("Error while closing the BAM file!");
+    fo_ = nullptr;
+}
+
+BamWriter::~BamWriter() { close(); }
+
+}  // namespace host

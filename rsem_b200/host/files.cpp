@@ -168,12 +168,13 @@ void load_refs(const std::string& path, bool with_seqs, RefData& r) {
 }
 
 // ---- ref.ti ---------------------------------------------------------------------------------------
-void load_transcripts(const std::string& path, std::vector<TranscriptInfo>& out) {
+void load_transcripts(const std::string& path, std::vector<TranscriptInfo>& out, int* type_out) {
     std::ifstream fin(path.c_str());
     if (!fin.is_open()) { fprintf(stderr, "Cannot open %s! It may not exist.\n", path.c_str()); exit(-1); }
     int M, type;
     std::string line;
     fin >> M >> type;
+    if (type_out) *type_out = type;
     getline(fin, line);
     out.assign(M + 1, TranscriptInfo());
     for (int i = 1; i <= M; ++i) {

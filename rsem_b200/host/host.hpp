@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <functional>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -48,7 +49,8 @@ struct TranscriptInfo {
     std::string transcript_id, transcript_name, gene_id, gene_name, seqname;
     int length = 0;
 };
-void load_transcripts(const std::string& path, std::vector<TranscriptInfo>& out);  // index 1..M
+// index 1..M; *type = 0 from a genome, 1 stand-alone transcriptome, 2 allele-specific (Transcripts.h:75)
+void load_transcripts(const std::string& path, std::vector<TranscriptInfo>& out, int* type = nullptr);
 void load_groups(const std::string& path, std::vector<int>& starts);               // GroupInfo.h:34-53
 bool load_allele_groups(const std::string& ref_name, std::vector<int>& gt, std::vector<int>& ta);  // WriteResults.h:106-123
 
@@ -156,6 +158,83 @@ void write_results_gibbs(const std::string& ref_name, const std::string& imd_nam
                          const std::vector<double>& pme_fpkm, const std::vector<double>& pme_tpm,
                          const std::vector<double>& pve_c, const std::vector<double>& pve_c_genes,
                          const std::vector<double>& pve_c_trans);  // WriteResults.h:357-479
+
+// ---- alignment files for -b: SAM / BAM in, BAM out (bam.cpp; BamWriter.h, sam_utils.h, SamHeader.cpp) -----------------
+struct BamRecord {
+    std::vector<uint8_t> data;  // the record as BAM stores it, without the leading block_size
+    uint16_t flag() const;
+    int32_t tid() const;
+    bool mapped() const { return !(flag() & 0x4); }
+    bool read1() const { return flag() & 0x40; }
+    void set_alignment_weight(double prb);  // MAPQ + ZW:f (BamWriter.h:39-48)
+};
+
+class AlnReader {
+public:
+    explicit AlnReader(const std::string& path);
+    ~AlnReader();
+    AlnReader(const AlnReader&) = delete;
+    AlnReader& operator=(const AlnReader&) = delete;
+    const std::string& header_text() const { return text_; }
+    const std::vector<std::string>& ref_names() const { return ref_names_; }
+    bool next(BamRecord& rec);  // false at the end of the file
+
+private:
+    struct Source;
+    Source* src_;
+    bool is_bam_ = false, have_pending_ = false;
+    std::string text_, pending_;
+    std::vector<std::string> ref_names_;
+    std::vector<uint32_t> ref_lens_;
+    std::map<std::string, int> ref_index_;
+    void parse_sam_line(const std::string& ln, BamRecord& rec) const;
+};
+
+std::string rsem_bam_header_text(const std::string& in_text);  // SamHeader(text) + insertPG("RSEM")
+
+class BamWriter {
+public:
+    BamWriter(const std::string& path, const std::string& header_text, int threads);
+    ~BamWriter();
+    BamWriter(const BamWriter&) = delete;
+    BamWriter& operator=(const BamWriter&) = delete;
+    void write(const BamRecord& rec);
+    void close();
+
+private:
+    FILE* fo_ = nullptr;
+    int threads_ = 1;
+    std::vector<uint8_t> pending_;
+    void append(const uint8_t* p, size_t n);
+    void flush_pending(bool all);
+};
+
+// boost::random::mt19937 as the reference uses it (sampling.h:12-16): engine(seed), 32-bit draws; uniform_01 = x * 2^-32
+struct Mt {
+    uint32_t mt[624];
+    int idx;
+    explicit Mt(uint32_t seed) {
+        mt[0] = seed;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int k = 0; k < 624; ++k) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    double uniform01() { return next() * (1.0 / 4294967296.0); }  // boost uniform_01 on a 32-bit engine
+};
 
 // ---- small utilities -----------------------------------------------------------------------------
 std::vector<char> slurp(const std::string& path, bool must_exist = true);

@@ -9,8 +9,10 @@
 //     the GPU is chosen with RSEM_B200_DEVICE (default 0), several GPUs with RSEM_B200_DEVICES=0,1,..:
 //     reads are sharded over them like the reference shards them over threads, counts and model
 //     statistics are summed with ncclAllReduce.
-//   * -b (posterior BAM output) is not implemented yet: the run stops with an
-//     error before doing any work, so the Perl driver must be called with --no-bam-output.
+//   * -b: the input SAM / BAM is re-read and written to sampleName.transcript.bam with MAPQ and ZW:f set from the
+//     posteriors (EM.cpp:504-536, BamWriter.h); SAM and BAM are read and BAM is written by this program's own
+//     BGZF / BAM code (host/bam.cpp) - CRAM input and the has_fai / fai_file arguments (which the reference parses but
+//     never applies, BamWriter.h:56) are not supported.  -p sets the BGZF compression threads like hts_set_threads.
 //   * RSEM_MAX_ROUND / RSEM_MIN_ROUND override the compile-time constants MAX_ROUND = 10000 and
 //     MIN_ROUND = 20 (EM.cpp:54-55), like oracle/_ref/rsem-run-em-rounds, for fixed-round parity runs.
 #include <algorithm>
@@ -20,6 +22,7 @@
 #include <chrono>
 #include <ctime>
 #include <future>
+#include <map>
 #include <thread>
 
 #include "host.hpp"
@@ -33,7 +36,97 @@ struct Args {
     int read_type = 0;
     bool genBam = false, bamSampling = false, gibbsOut = false, hasSeed = false, appendNames = false;
     uint32_t seed = 0;
+    std::string inpSamF;
 };
+
+// EM.cpp:504-536 + BamWriter::work (BamWriter.h:82-146): every mapped alignment line (pair of lines for paired-end
+// reads) takes the next hit's posterior, in .dat order; all lines are written back, mates with read 1 first.
+void write_posterior_bam(const Args& a, const std::vector<TranscriptInfo>& tr, int ti_type, const HitStore& hits,
+                         std::vector<double>& post, const std::vector<double>& post0, int threads) {
+    const int M = (int)tr.size() - 1;
+    if (a.bamSampling) {  // one alignment (or the noise entry) per read, drawn from its posterior (EM.cpp:507-531)
+        Mt engine(a.hasSeed ? a.seed : (uint32_t)time(NULL));
+        if (g_verbose) printf("Begin to sample reads from their posteriors.\n");
+        std::vector<double> arr;
+        for (uint64_t j = 0; j < hits.N; ++j) {
+            const uint64_t fr = hits.row_ptr[j], to = hits.row_ptr[j + 1];
+            const int len = (int)(to - fr + 1);
+            arr.assign(len, 0.0);
+            arr[0] = post0[j];
+            for (uint64_t k = fr; k < to; ++k) arr[k - fr + 1] = arr[k - fr] + post[k];
+            int id = -1;
+            if (!(arr[len - 1] < kEps)) {  // sample(): first index with arr[index] > u * total (sampling.h:50-65)
+                const double prb = engine.uniform01() * arr[len - 1];
+                int l = 0, r = len - 1;
+                while (l <= r) {
+                    const int mid = (l + r) / 2;
+                    if (arr[mid] <= prb) l = mid + 1;
+                    else r = mid - 1;
+                }
+                if (l >= len) die("sampling: the draw fell outside the cumulative posterior (reference: assert(l < len))");
+                id = l;
+            }
+            for (uint64_t k = fr; k < to; ++k) post[k] = ((int)(k - fr + 1) == id ? 1.0 : 0.0);
+        }
+        if (g_verbose) printf("Sampling is finished.\n");
+    }
+    AlnReader in(a.inpSamF);
+    // external reference index -> internal transcript id (Transcripts::buildMappings, Transcripts.h:105-143)
+    const std::vector<std::string>& names = in.ref_names();
+    if (names.empty()) die("The SAM/BAM file declares less than one reference sequence!");
+    if ((int)names.size() > M) die("The SAM/BAM file declares more reference sequences (" + std::to_string(names.size()) + ") than RSEM knows (" + std::to_string(M) + ")!");
+    if ((int)names.size() < M)
+        fprintf(stderr, "Warning: The SAM/BAM file declares less reference sequences (%d) than RSEM knows (%d)! Please make sure that you aligned your reads against transcript sequences instead of genome.\n", (int)names.size(), M);
+    std::map<std::string, int> dict;
+    for (int i = 1; i <= M; ++i) {
+        const std::string& tid = ti_type == 2 ? tr[i].seqname : tr[i].transcript_id;
+        if (!dict.emplace(tid, i).second) die("RSEM's indices might be corrupted, " + tid + " appears more than once!");
+    }
+    std::vector<int> e2i(names.size(), 0);
+    for (size_t i = 0; i < names.size(); ++i) {
+        auto it = dict.find(names[i]);
+        if (it == dict.end()) die("RSEM can not recognize reference sequence name " + names[i] + "!");
+        if (it->second < 0) die("Reference sequence name " + names[i] + " appears more than once in the SAM/BAM file!");
+        e2i[i] = it->second;
+        it->second = -1;
+    }
+    BamWriter out(a.outName + ".transcript.bam", rsem_bam_header_text(in.header_text()), threads);
+    const bool paired = a.read_type >= 2;
+    uint64_t next_hit = 0, cnt = 0;
+    auto take_hit = [&](const BamRecord& b) {
+        if (next_hit >= hits.H) die("The alignment file has more aligned lines than the .dat file has alignments (reference: assert(hit != NULL))!");
+        const int32_t t = b.tid();
+        if (t < 0 || t >= (int32_t)e2i.size() || e2i[t] != std::abs(hits.sid[next_hit]))
+            die("The alignment file does not match the .dat file (reference: assert(getInternalSid(tid + 1) == hit->getSid()))!");
+        return post[next_hit++];
+    };
+    BamRecord b, b2;
+    if (!paired) {
+        while (in.next(b)) {
+            ++cnt;
+            if (g_verbose && cnt % 1000000 == 0) printf("%llu alignment lines are loaded!\n", (unsigned long long)cnt);
+            if (b.mapped()) b.set_alignment_weight(take_hit(b));
+            out.write(b);
+        }
+    } else {
+        while (in.next(b) && in.next(b2)) {
+            cnt += 2;
+            if (g_verbose && cnt % 1000000 == 0) printf("%llu alignment lines are loaded!\n", (unsigned long long)cnt);
+            if (!b.read1()) b.data.swap(b2.data);
+            if (b.mapped() && b2.mapped()) {
+                const double w = take_hit(b);
+                if (b2.tid() != b.tid()) die("The two mates of a read pair align to different transcripts in the alignment file!");
+                b.set_alignment_weight(w);
+                b2.set_alignment_weight(w);
+            }
+            out.write(b);
+            out.write(b2);
+        }
+    }
+    if (next_hit != hits.H) die("The alignment file has fewer aligned lines than the .dat file has alignments (reference: assert(wrapper.getNextHit() == NULL))!");
+    out.close();
+    if (g_verbose) printf("Bam output file is generated!\n");
+}
 
 void usage() {
     printf("Usage : rsem-run-em refName read_type sampleName imdName statName [-p #Threads] [-b samInpF has_fai? [fai_file]] [-q] [--gibbs-out] [--sampling] [--seed seed] [--append-names]\n\n");
@@ -96,7 +189,7 @@ int main(int argc, char* argv[]) {
     int nThreads = 1;
     for (int i = 6; i < argc; ++i) {
         if (!strcmp(argv[i], "-p") && i + 1 < argc) nThreads = atoi(argv[i + 1]);
-        if (!strcmp(argv[i], "-b")) a.genBam = true;
+        if (!strcmp(argv[i], "-b") && i + 1 < argc) { a.genBam = true; a.inpSamF = argv[i + 1]; }
         if (!strcmp(argv[i], "-q")) g_verbose = false;
         if (!strcmp(argv[i], "--gibbs-out")) a.gibbsOut = true;
         if (!strcmp(argv[i], "--sampling")) a.bamSampling = true;
@@ -106,8 +199,6 @@ int main(int argc, char* argv[]) {
     if (nThreads <= 0) die("Number of threads should be bigger than 0!");
     g_io_threads = env_int("RSEM_B200_IO_THREADS", nThreads);   // -p: host threads for parsing / formatting
     if (a.read_type < 0 || a.read_type > 3) { fprintf(stderr, "Unknown Read Type!\n"); exit(-1); }
-    if (a.genBam)
-        die("rsem-run-em (B200): -b (posterior BAM output) is not implemented; run rsem-calculate-expression with --no-bam-output.");
 
     // CUDA context creation takes seconds on a multi-GPU node: start it now, overlap it with the file parsing
     struct CtxResult { int rc; rsem_b200_ctx* ctx; std::string err; };
@@ -122,7 +213,8 @@ int main(int argc, char* argv[]) {
     load_refs(a.refName + ".seq", true, refs);
     const int M = refs.M;
     std::vector<TranscriptInfo> transcripts;
-    load_transcripts(a.refName + ".ti", transcripts);
+    int ti_type = 0;
+    load_transcripts(a.refName + ".ti", transcripts, &ti_type);
     stamp("refs + transcripts loaded");
 
     uint64_t N0, N1, N2, N_tot;
@@ -145,6 +237,11 @@ int main(int argc, char* argv[]) {
         for (int i = 1; i <= M; ++i) eel[i] = transcripts[i].length;
         std::vector<double> countv(M + 1, 0.0);
         write_results_em(a.refName, a.imdName, transcripts, theta, eel, countv.data(), a.appendNames);
+        if (a.genBam) {  // EM.cpp:627-633: the input is copied as it is
+            const std::string command = "cp " + a.inpSamF + " " + a.outName + ".transcript.bam";
+            printf("%s\n", command.c_str());
+            if (system(command.c_str()) != 0) die("Cannot copy " + a.inpSamF + "!");
+        }
         const time_t t_end = time(NULL);
         printf("Time Used for EM.cpp : %d h %02d m %02d s\n", int((t_end - t_start) / 3600), int((t_end - t_start) % 3600 / 60), int((t_end - t_start) % 60));
         return 0;
@@ -206,6 +303,8 @@ int main(int argc, char* argv[]) {
     if (world > 1) check_rc(rsem_b200_comm_unique_id(uid), "comm_unique_id");
 
     std::vector<double> conprb(hits.H), ncpv(hits.N), counts(M + 1, 0.0);
+    std::vector<double> post, post0;  // posteriors in hit / read order, only kept for -b
+    if (a.genBam) { post.resize(hits.H); post0.resize(hits.N); }
     HostModel final_model;
     long long totNum = 0;
 
@@ -295,6 +394,7 @@ int main(int argc, char* argv[]) {
         std::vector<double> th(M + 1), cnt(M + 1);
         check_rc(rsem_b200_get_theta(ctx, th.data()), "get_theta");
         check_rc(rsem_b200_expected_weights(ctx, cnt.data()), "expected_weights");
+        if (a.genBam) check_rc(rsem_b200_download_conprb(ctx, post.data() + h0, post0.data() + r0), "download_conprb");  // now the posteriors
         if (rank == 0) {
             theta = th;
             counts = cnt;
@@ -331,6 +431,10 @@ int main(int argc, char* argv[]) {
     model.write(a.statName + ".model");
     write_results_em(a.refName, a.imdName, transcripts, theta, eel, counts.data(), a.appendNames);
     stamp(".theta / .model / result rows written");
+    if (a.genBam) {
+        write_posterior_bam(a, transcripts, ti_type, hits, post, post0, nThreads);
+        stamp("transcript BAM written");
+    }
 
     const time_t t_end = time(NULL);
     printf("Time Used for EM.cpp : %d h %02d m %02d s\n", int((t_end - t_start) / 3600), int((t_end - t_start) % 3600 / 60), int((t_end - t_start) % 60));

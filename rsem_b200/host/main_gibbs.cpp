@@ -21,32 +21,6 @@ using namespace host;
 
 namespace {
 
-// minimal host MT19937, only to derive the per-chain seeds like engineFactory (sampling.h:19-42)
-struct Mt {
-    uint32_t mt[624];
-    int idx;
-    explicit Mt(uint32_t seed) {
-        mt[0] = seed;
-        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
-        idx = 624;
-    }
-    uint32_t next() {
-        if (idx >= 624) {
-            for (int k = 0; k < 624; ++k) {
-                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
-                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            }
-            idx = 0;
-        }
-        uint32_t y = mt[idx++];
-        y ^= y >> 11;
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= y >> 18;
-        return y;
-    }
-};
-
 }  // namespace
 
 int main(int argc, char* argv[]) {

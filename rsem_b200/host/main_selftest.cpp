@@ -24,7 +24,31 @@ static void dump(const std::string& path, const std::vector<T>& v) {
     fclose(f);
 }
 
+// rsem-b200-host-selftest --bam-copy in.(sam|bam) out.bam threads [weight_step]
+// reads every record with AlnReader and writes it with BamWriter; with weight_step > 0 the k-th mapped record gets the
+// posterior (k * weight_step) mod 1 through set_alignment_weight (MAPQ + ZW:f), like rsem-run-em -b does.
+static int bam_copy(int argc, char** argv) {
+    if (argc < 5) { fprintf(stderr, "Usage: rsem-b200-host-selftest --bam-copy in out.bam threads [weight_step]\n"); return -1; }
+    const double step = argc > 5 ? atof(argv[5]) : 0.0;
+    AlnReader in(argv[2]);
+    BamWriter out(argv[3], rsem_bam_header_text(in.header_text()), atoi(argv[4]));
+    BamRecord r;
+    unsigned long long n = 0, mapped = 0;
+    while (in.next(r)) {
+        ++n;
+        if (step > 0 && r.mapped()) {
+            ++mapped;
+            r.set_alignment_weight(std::fmod((double)mapped * step, 1.0));
+        }
+        out.write(r);
+    }
+    out.close();
+    printf("records %llu mapped %llu refs %zu\n", n, mapped, in.ref_names().size());
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && std::string(argv[1]) == "--bam-copy") return bam_copy(argc, argv);
     if (argc != 6) {
         fprintf(stderr, "Usage: rsem-b200-host-selftest imdName read_type threads seedLen outPrefix\n");
         return -1;

@@ -44,8 +44,9 @@ def run_em(d, read_type, which, rounds=None, min_rounds=None, threads=1, gibbs_o
     if rounds is not None:
         env["RSEM_MAX_ROUND"] = str(rounds)
         env["RSEM_MIN_ROUND"] = str(min_rounds if min_rounds is not None else min(20, rounds))
-    if which == "ref":
-        exe = os.path.join(REF_DIR, "rsem-run-em-rounds")
+    if which in ("ref", "ref_unpatched"):
+        # "ref_unpatched": oracle/_ref/rsem-run-em, the reference compiled without the MAX/MIN_ROUND environment hook
+        exe = os.path.join(REF_DIR, "rsem-run-em-rounds" if which == "ref" else "rsem-run-em")
         subprocess.check_call([os.path.join(REF_DIR, "rsem-build-read-index"), "32", str(read_type & 1), "1", *read_files(d, read_type)])
     else:
         exe = os.path.join(BIN_DIR, "rsem-run-em")

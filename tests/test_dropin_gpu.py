@@ -126,10 +126,37 @@ def test_no_alignable_reads(workdir):
     assert filecmp.cmp(f"{ref}/s.temp/s.gene_res", f"{ours}/s.temp/s.gene_res", shallow=False)
 
 
-def test_bam_flag_is_refused_loudly(workdir):
-    base = rf.gen_dataset(str(workdir / "bam_base"), read_type=0, M=30, N1=100, N0=5)
-    p = rf.run_em(base, 0, "ours", rounds=2, extra=["-b", "x.bam", "0"], check=False)
-    assert p.returncode != 0 and "-b" in p.stderr
+@pytest.mark.parametrize("rt,sampling", [(3, False), (0, False), (1, True)])
+def test_posterior_bam(workdir, rt, sampling):
+    """-b (EM.cpp:504-536, BamWriter.h): every alignment line of the input comes back with MAPQ and ZW:f from the posteriors;
+    --sampling draws one alignment per read with the seeded MT19937 (sampling.h:50-65)"""
+    from bam_reader import read_bam
+    base = rf.gen_dataset(str(workdir / f"bam_base_{rt}"), read_type=rt, M=80, N1=1500, N0=70, read_len=50, sam=1, seed=13 + rt)
+    ref, ours = rf.clone(base, str(workdir / f"bam_ref_{rt}")), rf.clone(base, str(workdir / f"bam_ours_{rt}"))
+    extra = ["-b", "aln.sam", "0"] + (["--sampling", "--seed", "4242"] if sampling else [])
+    rf.run_em(ref, rt, "ref", rounds=13, threads=2, gibbs_out=False, extra=extra)
+    po = rf.run_em(ours, rt, "ours", rounds=13, threads=3, gibbs_out=False, extra=extra)
+    assert "Bam output file is generated!" in po.stdout
+    tr, rr, a = read_bam(f"{ref}/s.transcript.bam")
+    to, ro, b = read_bam(f"{ours}/s.transcript.bam")
+    assert (tr, rr) == (to, ro) and len(a) == len(b)
+    for x, y in zip(b, a):
+        zx, zy = x["tags"].pop("ZW", None), y["tags"].pop("ZW", None)
+        assert (zx is None) == (zy is None) == bool(y["flag"] & 4)
+        if zy is not None:
+            assert abs(zx[1] - zy[1]) <= 1e-6 + 1e-6 * abs(zy[1])
+            if sampling:
+                assert zx[1] in (0.0, 1.0)
+            assert abs(x["mapq"] - y["mapq"]) <= (0 if zx[1] == zy[1] else 1)
+            x["mapq"] = y["mapq"]
+        assert x == y
+
+
+def test_bam_of_a_sample_without_alignable_reads(workdir):
+    """N1 == 0 with -b: the input file is copied as it is (EM.cpp:627-633)"""
+    base = rf.gen_dataset(str(workdir / "bam_n1zero"), read_type=0, M=30, N1=0, N0=50, sam=1)
+    rf.run_em(base, 0, "ours", rounds=3, gibbs_out=False, extra=["-b", "aln.sam", "0"])
+    assert filecmp.cmp(f"{base}/aln.sam", f"{base}/s.transcript.bam", shallow=False)
 
 
 def test_em_two_gpus_matches_reference(workdir):

@@ -70,6 +70,8 @@ struct Cfg {
     double frag_mean = -1, frag_sd = 0;
     int omit = 0;             // number of trailing transcripts listed in .omit (never hit)
     double nfrac = 0.002;     // probability of an 'N' base call
+    int sam = 0;              // also write <out>/aln.sam: the same reads and alignments as a SAM file the unmodified
+                              // rsem-parse-alignments accepts (SamParser.h:122-265), for runs through rsem-calculate-expression
 };
 
 const char BASES[5] = {'A', 'C', 'G', 'T', 'N'};
@@ -108,7 +110,7 @@ void sequence(Rng& g, const std::string& tmpl, double nfrac, std::string& seq, s
     }
 }
 
-struct Hit { int sid, pos, insertL; };
+struct Hit { int sid, pos, insertL, fwd; };  // fwd: forward-strand start of the fragment on the transcript
 
 void die(const char* msg) { fprintf(stderr, "gen_dataset: %s\n", msg); exit(2); }
 FILE* xopen(const std::string& p) {
@@ -150,6 +152,7 @@ int main(int argc, char** argv) {
         else if (k == "--frag-sd") c.frag_sd = atof(v);
         else if (k == "--omit") c.omit = atoi(v);
         else if (k == "--nfrac") c.nfrac = atof(v);
+        else if (k == "--sam") c.sam = atoi(v);
         else { fprintf(stderr, "gen_dataset: unknown option %s\n", k.c_str()); return 2; }
     }
     const bool paired = c.read_type >= 2, hasQ = (c.read_type & 1);
@@ -257,6 +260,13 @@ int main(int argc, char** argv) {
         else fprintf(f, ">%s%ld/%d\n%s\n", tag, id, mate, s.c_str());
     };
 
+    FILE* fsam = nullptr;
+    if (c.sam) {
+        fsam = xopen(c.out + "/aln.sam");
+        fprintf(fsam, "@HD\tVN:1.0\tSO:unsorted\n");
+        for (int t = 1; t <= c.M; ++t) fprintf(fsam, "@SQ\tSN:T%d\tLN:%d\n", t, (int)tseq[t].size() + c.polyA);
+        fprintf(fsam, "@PG\tID:gen_dataset\n");
+    }
     // .dat body goes to a temp buffer file first because the header needs nHits
     std::string datp = c.out + "/s.temp/s.dat";
     FILE* fd = xopen(datp + ".body");
@@ -287,7 +297,7 @@ int main(int argc, char** argv) {
             else continue;
             int totLen = (int)tseq[t].size() + c.polyA;
             int pos = dir == 0 ? p : totLen - p - flen;     // strand-local coordinate
-            hits.push_back({dir == 0 ? t : -t, pos, flen});
+            hits.push_back({dir == 0 ? t : -t, pos, flen, p});
         }
         std::string frag = tseq[src].substr(fpos, flen);
         if (dir == 1) frag = revcomp(frag);
@@ -299,7 +309,7 @@ int main(int argc, char** argv) {
             if (flen <= (int)tseq[t].size()) {
                 int d2 = g.below(2);
                 int p = g.below((int)tseq[t].size() - flen + 1);
-                hits.push_back({d2 == 0 ? t : -t, d2 == 0 ? p : totLen - p - flen, flen});
+                hits.push_back({d2 == 0 ? t : -t, d2 == 0 ? p : totLen - p - flen, flen, p});
             }
         }
         fprintf(fd, "%zu", hits.size());
@@ -311,6 +321,25 @@ int main(int argc, char** argv) {
         nHits += hits.size();
         put(fr[0], "r", r, 1, s1, q1);
         if (paired) put(fr[1], "r", r, 2, s2, q2);
+        if (fsam) {  // all alignments of a read adjacent; reverse-strand records carry the reverse complement (SAM convention)
+            const std::string rs1 = revcomp(s1), rq1(q1.rbegin(), q1.rend()), rs2 = paired ? revcomp(s2) : std::string(),
+                              rq2 = paired ? std::string(q2.rbegin(), q2.rend()) : std::string();
+            for (auto& h : hits) {
+                const int t = std::abs(h.sid);
+                const bool rev = h.sid < 0;
+                if (!paired) {
+                    fprintf(fsam, "r%ld\t%d\tT%d\t%d\t255\t%dM\t*\t0\t0\t%s\t%s\n", r, rev ? 16 : 0, t, h.fwd + 1, L1,
+                            rev ? rs1.c_str() : s1.c_str(), hasQ ? (rev ? rq1.c_str() : q1.c_str()) : "*");
+                } else {
+                    const int p1 = rev ? h.fwd + h.insertL - L1 + 1 : h.fwd + 1;  // mate 1: 1-based leftmost forward coordinate
+                    const int p2 = rev ? h.fwd + 1 : h.fwd + h.insertL - L2 + 1;
+                    fprintf(fsam, "r%ld\t%d\tT%d\t%d\t255\t%dM\t=\t%d\t%d\t%s\t%s\n", r, rev ? 83 : 99, t, p1, L1, p2,
+                            rev ? -h.insertL : h.insertL, rev ? rs1.c_str() : s1.c_str(), hasQ ? (rev ? rq1.c_str() : q1.c_str()) : "*");
+                    fprintf(fsam, "r%ld\t%d\tT%d\t%d\t255\t%dM\t=\t%d\t%d\t%s\t%s\n", r, rev ? 163 : 147, t, p2, L2, p1,
+                            rev ? h.insertL : -h.insertL, rev ? s2.c_str() : rs2.c_str(), hasQ ? (rev ? q2.c_str() : rq2.c_str()) : "*");
+                }
+            }
+        }
     }
     fclose(fd);
     for (long r = 0; r < c.N0; ++r) {   // unalignable (noise) reads
@@ -322,7 +351,15 @@ int main(int argc, char** argv) {
             sequence(g, randseq(g, L2), c.nfrac, s2, q2);
             put(fu[1], "u", r, 2, s2, q2);
         }
+        if (fsam) {
+            if (!paired) fprintf(fsam, "u%ld\t4\t*\t0\t0\t*\t*\t0\t0\t%s\t%s\n", r, s1.c_str(), hasQ ? q1.c_str() : "*");
+            else {
+                fprintf(fsam, "u%ld\t77\t*\t0\t0\t*\t*\t0\t0\t%s\t%s\n", r, s1.c_str(), hasQ ? q1.c_str() : "*");
+                fprintf(fsam, "u%ld\t141\t*\t0\t0\t*\t*\t0\t0\t%s\t%s\n", r, s2.c_str(), hasQ ? q2.c_str() : "*");
+            }
+        }
     }
+    if (fsam) fclose(fsam);
     for (int i = 0; i < 2; ++i) { if (fr[i]) fclose(fr[i]); if (fu[i]) fclose(fu[i]); }
 
     {   // .dat = 100-char padded header + body (parseIt.cpp:197-211)

@@ -11,3 +11,4 @@ for f in gpurun_out/r2c_c3_*.log; do echo "$f: $(grep -o '"k2_ms_per_launch": [0
 ncu --set full --clock-control none --import-source on -k regex:estep_class -s 3 -c 1 -o gpurun_out/r2c_k2_class_c3 python bench.py --steps 3 --no-cpu-baseline --no-e2e --no-traffic > gpurun_out/r2c_ncu_full.log 2>&1
 python bench.py > gpurun_out/r2c_bench_default.log 2>&1
 tail -c 3000 gpurun_out/r2c_bench_default.log
+python -m pytest tests/test_baseline_sizes_gpu.py -x -q --durations=8 > gpurun_out/r2c_baseline_tests.log 2>&1; tail -15 gpurun_out/r2c_baseline_tests.log
