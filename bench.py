@@ -473,12 +473,22 @@ def run_ours(args):
         bytes_in = hr.numel() * 8 + hsid.numel() * 4 + hc.numel() * 8 + hn.numel() * 8 + (M + 1) * 8
         bytes_out = (M + 1) * 8
 
+        phases = {}
+
         def job(rounds):
+            t = [time.perf_counter()]
             ctx.upload_hits_ptr(N, H, M, hr.data_ptr(), hsid.data_ptr())
+            t.append(time.perf_counter())
             ctx.upload_conprb_ptr(hc.data_ptr(), hn.data_ptr())
+            t.append(time.perf_counter())
             ctx.set_theta(theta0)
             ctx.em_rounds(12, rounds, BIG, BIG, n0)
-            return ctx.get_theta()
+            t.append(time.perf_counter())
+            th = ctx.get_theta()
+            t.append(time.perf_counter())
+            phases[rounds] = {"upload_hits": round(t[1] - t[0], 4), "upload_conprb": round(t[2] - t[1], 4),
+                              "class_layout_and_rounds": round(t[3] - t[2], 4), "get_theta": round(t[4] - t[3], 4)}
+            return th
 
         res = {}
         for rounds in E2E_ROUNDS:
@@ -499,7 +509,7 @@ def run_ours(args):
         r0 = E2E_ROUNDS[0]
         e2e = {"value": res[r0][0], "unit": "hits/s", "h2d_bytes_per_step": bytes_in // r0, "d2h_bytes_per_step": bytes_out // r0,
                "h2d_bytes_per_job": bytes_in, "d2h_bytes_per_job": bytes_out, "rounds_per_job": r0, "jobs": 2,
-               "seconds_per_job": round(res[r0][1], 4),
+               "seconds_per_job": round(res[r0][1], 4), "phases_s_last_job": phases[r0],
                "note": "job = upload CSR + conprb from pinned host memory, build tiles and the class layout, run the rounds, "
                        "read theta back; a step is one round, so the per-step bytes are the job's bytes / rounds_per_job"}
         for rounds in E2E_ROUNDS[1:]:

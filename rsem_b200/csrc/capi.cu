@@ -48,6 +48,8 @@ void free_hits(rsem_b200_ctx* c) {
     if (c->wtile_hit) { cudaFree(c->wtile_hit); c->wtile_hit = nullptr; }
     c->n_tiles = c->n_wtiles = 0;
     class_free(c);
+    if (c->reads.uni) { cudaFree(c->reads.uni); c->reads.uni = nullptr; }   // sized by N, derived from the hits
+    c->reads.uni_valid = false;
     c->N = c->H = 0;
     c->conprb_valid = false;
     c->conprb_epoch++;
@@ -60,6 +62,8 @@ void free_reads(rsem_b200_ctx* c) {
         if (c->reads.qual[m]) { cudaFree(c->reads.qual[m]); c->reads.qual[m] = nullptr; }
     }
     if (c->reads.lowq) { cudaFree(c->reads.lowq); c->reads.lowq = nullptr; }
+    if (c->reads.uni) { cudaFree(c->reads.uni); c->reads.uni = nullptr; }
+    c->reads.uni_valid = false;
     c->reads.n_mates = 0;
 }
 
@@ -71,6 +75,7 @@ void free_refs(rsem_b200_ctx* c) {
     if (c->refs.mask_off) cudaFree(c->refs.mask_off);
     if (c->refs.mask_words) cudaFree(c->refs.mask_words);
     c->refs = DevRefs{};
+    c->reads.uni_valid = false;
 }
 
 void free_gibbs(rsem_b200_ctx* c) {
@@ -82,7 +87,6 @@ void free_gibbs(rsem_b200_ctx* c) {
     if (c->gibbs.p_sid) cudaFree(c->gibbs.p_sid);
     if (c->gibbs.p_con) cudaFree(c->gibbs.p_con);
     if (c->gibbs.seg_start) cudaFree(c->gibbs.seg_start);
-    if (c->gibbs.blk_seg) cudaFree(c->gibbs.blk_seg);
     c->gibbs = DevGibbs{};
 }
 
@@ -110,6 +114,8 @@ int finish_matrix_setup(rsem_b200_ctx* ctx) {
     RB_CUDA(cudaMemsetAsync(ctx->theta, 0, ((size_t)ctx->M + 1) * sizeof(double), ctx->stream));
     RB_CUDA(cudaMemsetAsync(ctx->count, 0, ((size_t)ctx->M + 1) * sizeof(double), ctx->stream));
     RB_CUDA(cudaMemsetAsync(ctx->done_flag, 0, sizeof(int), ctx->stream));
+    ctx->k2_target = ctx->count;
+    if (ctx->comm) if (int rc = p2p_setup(ctx)) return rc;   // collective: every rank uploads its shard
     return em_build_tiles(ctx);
 }
 
@@ -140,6 +146,10 @@ int check_err_flag(rsem_b200_ctx* ctx) {
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (e) {
         RB_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+        if (e == 4) {
+            set_error("a peer GPU never reported its counts of the round (count reduction over NVLink peer memory): a rank has failed");
+            return RSEM_B200_ERR_NCCL;
+        }
         set_error(e == 2 ? "an alignment lies outside its transcript (the reference aborts here: general_assert in "
                            "getConPrb, e.g. SingleQModel.h:116-121); the aligner may have reported different read "
                            "lengths for the same read"
@@ -207,6 +217,7 @@ int rsem_b200_ctx_destroy(rsem_b200_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    p2p_release(c);
     if (c->comm) nccl_comm_destroy(c->comm);
     if (c->phase_timing) {
         static const char* names[3] = {"K1 conprb_kernel", "K2 E-step with posteriors", "K3 model statistics"};
@@ -262,6 +273,7 @@ int rsem_b200_comm_init(rsem_b200_ctx* c, const void* id, int n_ranks, int rank)
     RB_ARG(c && id, "NULL argument");
     RB_ARG(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad rank / n_ranks");
     RB_CUDA(cudaSetDevice(c->device));
+    p2p_release(c);
     if (c->comm) { nccl_comm_destroy(c->comm); c->comm = nullptr; }
     c->n_ranks = n_ranks;
     c->rank = rank;
@@ -516,8 +528,16 @@ int rsem_b200_em_rounds(rsem_b200_ctx* c, int32_t first_round, int32_t max_round
     if (int rc = ensure_stats(c, n)) return rc;
     RB_CUDA(cudaMemsetAsync(c->d_stats, 0xff, sizeof(rsem_b200_round_stats) * n, c->stream));  // totnum = -1 marks "not run"
     for (int r = 0; r < n; ++r) {
-        if (int rc = em_launch_estep(c, false)) return rc;
-        if (c->comm) if (int rc = nccl_allreduce_sum_f64(c->comm, c->count, (size_t)c->M + 1, c->stream)) return rc;
+        if (c->p2p.on) {   // counts summed over NVLink peer memory, folded into the round's kernels (p2p.cu)
+            c->k2_target = p2p_k2_target(c);
+            const int rc = em_launch_estep(c, false);
+            c->k2_target = c->count;
+            if (rc) return rc;
+            if (int rc2 = p2p_reduce(c)) return rc2;
+        } else {
+            if (int rc = em_launch_estep(c, false)) return rc;
+            if (c->comm) if (int rc = nccl_allreduce_sum_f64(c->comm, c->count, (size_t)c->M + 1, c->stream)) return rc;
+        }
         if (int rc = em_launch_theta_update(c, n0, first_round + r, min_round, max_round, r)) return rc;
     }
     std::vector<rsem_b200_round_stats> h(n);

@@ -980,7 +980,7 @@ int class_launch_estep(rsem_b200_ctx* ctx) {
         a.tile = static_cast<const TileRec*>(L.tile);
         a.n_tiles = L.n_tiles;
         a.theta = ctx->theta;
-        a.count = ctx->count;
+        a.count = ctx->k2_target;
         a.done_flag = ctx->done_flag;
         if (!L.cta_ns) {
             RB_CUDA(cudaMalloc(&L.cta_ns, (size_t)ctx->sm_count * sizeof(unsigned long long)));
@@ -1012,7 +1012,7 @@ int class_launch_estep(rsem_b200_ctx* ctx) {
     if (L.n_long) {
         estep_long_rows_kernel<<<std::min<unsigned>(L.n_long, (unsigned)ctx->sm_count * 4), 256, 0, ctx->stream>>>(
             reinterpret_cast<const unsigned long long*>(ctx->row_ptr), ctx->sid_abs, ctx->conprb, ctx->ncpv, L.long_rows, L.n_long,
-            ctx->theta, ctx->count, ctx->done_flag);
+            ctx->theta, ctx->k2_target, ctx->done_flag);
         RB_CUDA(cudaGetLastError());
         ctx->launches++;
     }

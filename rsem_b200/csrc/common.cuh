@@ -38,6 +38,7 @@ const NcclApi* nccl_api();  // nullptr + last_error set when libnccl.so.2 cannot
 int nccl_unique_id(void* id128);
 int nccl_comm_init(void** comm, const void* id128, int n_ranks, int rank);
 int nccl_allreduce_sum_f64(void* comm, double* buf, size_t n, cudaStream_t stream);
+int nccl_allgather_bytes(void* comm, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream);
 int nccl_comm_destroy(void* comm);
 
 // ---- device-side model (pointers into one packed device buffer) -----------------------------
@@ -75,6 +76,8 @@ struct DevReads {
     uint8_t* base[2] = {nullptr, nullptr};
     uint8_t* qual[2] = {nullptr, nullptr};
     uint8_t* lowq = nullptr;
+    uint8_t* uni = nullptr;                 // per read: all hits show the same bases (model_kernels.cu); needs hits + refs too
+    bool uni_valid = false;
     int max_len = 0;
     int qmax = -1;                          // largest quality value (computed on first use)
     unsigned long long total_bases[2] = {0, 0};
@@ -96,15 +99,28 @@ struct DevGibbs {
     uint64_t* row_ptr = nullptr;
     int32_t* sid = nullptr;
     double* conprb = nullptr;
-    // component-parallel sampler (gibbs_kernels.cu): reads of a block grouped by connected component
-    int32_t* order = nullptr;      // N1 read ids: block by block, inside a block by (component, read id)
+    // component-parallel sampler (gibbs_kernels.cu): reads grouped by connected component
+    int32_t* order = nullptr;      // N1 read ids: component by component (longest first), read order inside
     uint64_t* p_off = nullptr;     // rows re-laid in that slot order
     int32_t* p_sid = nullptr;
     double* p_con = nullptr;
     int32_t* seg_start = nullptr;  // n_segs + 1 offsets into `order`
-    int32_t* blk_seg = nullptr;    // n_blocks + 1 segment ranges
-    int32_t block_reads = 0, n_blocks = 0, n_segs = 0;
+    int32_t n_segs = 0;
     uint32_t max_len = 0;
+};
+
+// count reduction over NVLink peer memory (p2p.cu)
+constexpr int kMaxP2PRanks = 8;
+struct P2PState {
+    bool on = false;
+    int n = 0;
+    uint64_t seq = 0;                       // rounds reduced so far (same on every rank): buffer parity + flag value
+    double* count_buf = nullptr;            // 2 x (M + 1): K2 accumulates into [(seq + 1) & 1]
+    unsigned long long* flags = nullptr;    // flags[r] = last round rank r has completed
+    double* peer_count[kMaxP2PRanks] = {};
+    unsigned long long* peer_flags[kMaxP2PRanks] = {};
+    void* opened_count[kMaxP2PRanks] = {};  // cudaIpcOpenMemHandle results to close
+    void* opened_flags[kMaxP2PRanks] = {};
 };
 
 // equivalence-class layout of the hit matrix for the frozen-conprb rounds (class_kernels.cu)
@@ -194,6 +210,8 @@ struct rsem_b200_ctx {
     // multi-GPU
     void* comm = nullptr;
     int n_ranks = 1, rank = 0;
+    rsem_b200::P2PState p2p;
+    double* k2_target = nullptr;   // where K2 accumulates (count, or the peer-mapped buffer of the round)
 
     // RSEM_B200_PHASE_TIMING=1: device time per kernel of the model rounds (K1, K2 with posteriors, K3), printed at destroy
     bool phase_timing = false;
@@ -246,6 +264,12 @@ void class_free(rsem_b200_ctx* ctx);
 int class_build(rsem_b200_ctx* ctx);
 int class_fill_vals(rsem_b200_ctx* ctx);
 int class_launch_estep(rsem_b200_ctx* ctx);
+
+// p2p.cu
+void p2p_release(rsem_b200_ctx* ctx);
+int p2p_setup(rsem_b200_ctx* ctx);
+double* p2p_k2_target(rsem_b200_ctx* ctx);
+int p2p_reduce(rsem_b200_ctx* ctx);
 
 // model_kernels.cu
 int model_launch_conprb(rsem_b200_ctx* ctx);

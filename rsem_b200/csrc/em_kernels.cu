@@ -1249,7 +1249,7 @@ int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
     a.conprb = ctx->conprb;
     a.ncpv = ctx->ncpv;
     a.theta = ctx->theta;
-    a.count = ctx->count;
+    a.count = ctx->k2_target;
     a.post = ctx->post;
     a.post0 = ctx->post0;
     a.tile_row = reinterpret_cast<const unsigned long long*>(ctx->tile_row);

@@ -248,42 +248,45 @@ __global__ void __launch_bounds__(kGibbsThreads) gibbs_chain_kernel(const GibbsA
 // read x transcript graph (noise transcript 0 excluded) touch disjoint counts and commute exactly.  The only
 // global coupling is the noise count c0 = counts[0], which enters every row that has a noise entry.
 //
-//   * Static, once per upload (gibbs_prepare, host): connected components (union-find over transcripts), the
-//     read sequence cut into blocks of `block_reads` consecutive reads, the reads of a block grouped by
-//     component in read order ("segments").
-//   * Per block, per chain: every segment is walked by ONE thread in read order with the live counts of its
-//     component and a SNAPSHOT of c0 taken at the start of the pass.  That is exactly the sequential result as
-//     long as no read of the block changes its noise membership.  Reads that do are recorded (atomicMin of their
-//     position p); after the pass everything after p is rolled back (z from the saved copy, counts re-adjusted -
-//     both component-private) and re-run with the corrected c0.  Each iteration is exact up to and including the
-//     next membership change, so the loop ends with the sequential state, bit for bit.
-//   * The i-th uniform of a sweep is the (sweep * N1 + i)-th output of the chain's MT19937; CTA 0 of the chain
-//     produces the block's uniforms (624-word regeneration by the whole CTA) before the pass.
-//   * A chain is served by `ctas_per_chain` co-resident CTAs (cooperative launch) that meet at a per-chain
-//     barrier in global memory; chains never synchronise with each other.
+//   * Static, once per upload (gibbs_prepare, host): connected components (union-find over transcripts); the reads
+//     grouped by component in read order ("segments", longest first); rows re-laid in that slot order.
+//   * A sweep of a chain: every segment is walked by ONE thread in read order with the live counts of its component
+//     (component-private, plain loads / stores).  The noise count read i must see is c0(i) = c0 at the start of the
+//     sweep + (#reads before i that joined the noise transcript) - (#reads before i that left it).  Those "flips" are
+//     rare, so the sweep is a fixed-point iteration over the SET of flips:
+//         pass k walks all segments with c0(i) taken from the flips recorded by pass k - 1 (none for k = 0) and
+//         records its own flips (two bitmaps over read positions);
+//         if pass k recorded exactly the flips it was given, every read saw the noise count the sequential sweep
+//         would have shown it - by induction over the read positions the draws ARE the sequential draws - done;
+//         otherwise the counts are restored from the copy taken at the start of the sweep and pass k + 1 runs.
+//     A draw changes with c0 only when u * total falls into the sliver by which the noise entry moved, so the
+//     iteration ends after two passes almost always (one when no read changed its noise membership).
+//   * The i-th uniform of sweep s is output s * N1 + i of the chain's MT19937.  A dedicated generator CTA per chain
+//     runs one sweep ahead of the workers (624-word regenerations, 227 threads wide, ping-pong state in shared memory).
+//   * A chain is served by `ctas_per_chain` worker CTAs + 1 generator CTA, all co-resident (cooperative launch); the
+//     workers meet at a per-chain barrier in global memory a handful of times per sweep (not once per block of reads);
+//     chains never synchronise with each other.
 // ================================================================================================
 constexpr int kPThreads = 256;
 
 struct ChainSync {
-    unsigned count, gen;       // barrier among the chain's CTAs
-    unsigned flip[2];          // smallest read position whose noise membership changed in the current pass
+    unsigned count, gen;        // barrier among the chain's worker CTAs
+    unsigned u_ready;           // generator -> workers: uniforms of sweeps < u_ready are complete
+    unsigned sweeps_done;       // workers -> generator: sweeps < sweeps_done no longer need their uniform buffer
+    unsigned changed;           // some flip word differs between the pass's input and output sets
     int err;
-    unsigned pad[3];
-    unsigned long long prof[8];   // clock64 totals of CTA 0: rng, copy+barrier, pass, pass barrier, rollback, samples
+    unsigned passes, pad;       // diagnostics: passes run over all sweeps
+    unsigned long long prof[4]; // clock64 totals of worker CTA 0: wait for uniforms, passes, barriers + bookkeeping, per-sample work
 };
 
 struct PArgs {
     unsigned long long N1;
-    const unsigned long long* row_ptr;
-    const int* sid;
-    const double* conprb;
-    const int* order;                   // read id of slot q (block by block, inside a block by component)
+    const int* order;                   // read id of slot q (component by component, read order inside)
     const unsigned long long* p_off;    // N1 + 1 entry offsets of the slots, rows stored in slot order
     const int* p_sid;
     const double* p_con;
-    const int* seg_start;
-    const int* blk_seg;
-    int block_reads, n_blocks;
+    const int* seg_start;               // n_segs + 1 slot offsets
+    int n_segs;
     int M, burnin, gap, n_genes, n_chains, ctas_per_chain, chain_base;
     const int* chain_samples;
     const unsigned* chain_seeds;
@@ -295,9 +298,13 @@ struct PArgs {
     const double* mw;
     const int* gene_start;
     int* counts;           // n_chains * (M + 1)
-    int* z;                // n_chains * N1, indexed by SLOT (not by read id)
-    int* zsave;            // n_chains * block_reads
-    unsigned* ublk;        // n_chains * 2 * block_reads raw MT outputs (double buffered)
+    int* counts_start;     // n_chains * (M + 1): copy taken at the start of a sweep
+    int* z;                // n_chains * 2 * N1, indexed by SLOT; [sweep parity]
+    unsigned* ubuf;        // n_chains * 2 * N1 raw MT outputs; [sweep parity]
+    unsigned* flips;       // n_chains * 4 * W words: [set 0 / 1][joined / left]
+    int* pre;              // n_chains * W: net flips in the words before w inside its CTA slice
+    int* slice_tot;        // n_chains * ctas_per_chain: net flips of every CTA slice
+    unsigned n_words;      // W = ceil(N1 / 32)
     ChainSync* sync;       // n_chains
     int* count_vectors;
     double* acc;
@@ -324,43 +331,85 @@ __device__ void chain_barrier(ChainSync* s, unsigned n_ctas) {
     __syncthreads();
 }
 
-// regenerate the 624 MT words with the whole CTA (three dependent phases + the last word)
-__device__ void mt_regenerate_cta(MtState& s) {
-    const int lo[4] = {0, 227, 454, 623}, hi[4] = {227, 454, 623, 624};
-    for (int p = 0; p < 4; ++p) {
-        const int k = lo[p] + (int)threadIdx.x;
-        unsigned v = 0;
-        if (k < hi[p]) v = mt_twist(s.mt[k], s.mt[(k + 1) % 624], s.mt[(k + 397) % 624]);
+// ---- generator CTA: the chain's MT19937, at most one sweep ahead of the workers ----------------------------------------
+// The state ping-pongs between two shared-memory arrays: a phase reads only words that are already final, so one
+// __syncthreads per phase (four per 624 outputs) is all the ordering it needs.  Output g of the stream belongs to
+// sweep g / N1, position g % N1, and goes to that sweep's buffer ([sweep parity]).
+__device__ void generator_loop(const PArgs& a, ChainSync* sy, unsigned* ubuf, unsigned n_sweeps, unsigned seed) {
+    __shared__ unsigned st[2][624];
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) {  // init_genrand (boost mt19937 seeding)
+        st[0][0] = seed;
+        for (int k = 1; k < 624; ++k) st[0][k] = 1812433253u * (st[0][k - 1] ^ (st[0][k - 1] >> 30)) + (unsigned)k;
+    }
+    __syncthreads();
+    int cur = 0;
+    const unsigned long long total = (unsigned long long)n_sweeps * a.N1;
+    unsigned acquired = 1;   // sweeps 0 and 1 own fresh buffers
+    unsigned published = 0;
+    for (unsigned long long g0 = 0; g0 < total; g0 += 624) {
+        const unsigned* o = st[cur];
+        unsigned* n = st[cur ^ 1];
+        if (tid < 227) n[tid] = mt_twist(o[tid], o[tid + 1], o[tid + 397]);                 // k in [0, 227)
         __syncthreads();
-        if (k < hi[p]) s.mt[k] = v;
+        if (tid < 227) n[227 + tid] = mt_twist(o[227 + tid], o[228 + tid], n[tid]);         // k in [227, 454)
         __syncthreads();
+        if (tid < 169) n[454 + tid] = mt_twist(o[454 + tid], o[455 + tid], n[227 + tid]);   // k in [454, 623)
+        __syncthreads();
+        if (tid == 0) n[623] = mt_twist(o[623], n[0], n[396]);                              // k = 623
+        __syncthreads();
+        cur ^= 1;
+        const unsigned take = (unsigned)min((unsigned long long)624, total - g0);
+        const unsigned sweep_hi = (unsigned)((g0 + take - 1) / a.N1);
+        if (sweep_hi > acquired) {   // first touch of a recycled buffer: the sweep two before must be finished
+            if (tid == 0) {
+                while (*((volatile unsigned*)&sy->sweeps_done) + 1 < sweep_hi) {}
+                __threadfence();
+            }
+            __syncthreads();
+            acquired = sweep_hi;
+        }
+        const unsigned sweep_lo = (unsigned)(g0 / a.N1);
+        const unsigned long long pos_lo = g0 - (unsigned long long)sweep_lo * a.N1;
+        for (unsigned k = tid; k < take; k += kPThreads) {
+            unsigned long long pos = pos_lo + k;
+            unsigned sw = sweep_lo;
+            while (pos >= a.N1) { pos -= a.N1; ++sw; }   // at most one step unless N1 < 624
+            __stcg(ubuf + (size_t)(sw & 1u) * a.N1 + pos, mt_temper(st[cur][k]));
+        }
+        const unsigned complete = (unsigned)((g0 + take) / a.N1);   // sweeps whose last output has been written
+        if (complete > published) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(&sy->u_ready, complete);
+            published = complete;
+        }
     }
 }
 
-// A thread walks the reads of one (block, component) segment in order.  The static part of a read (ids, conprb,
-// its uniform, its previous assignment) does not depend on the counts, so the next read's row is loaded into
-// registers while the current one is drawn: the only memory round trip left on the dependent chain of a read is
-// the gather of its candidates' counts.  Rows of up to kRowRegs entries take this register path; longer rows take
-// the generic two-pass loop that recomputes the same running sum, bit for bit.
+// A thread walks the reads of one component (segment) in order.  The static part of a read (ids, conprb, its
+// uniform, its previous assignment) does not depend on the counts, so the next read's row is loaded into registers
+// while the current one is drawn: the only memory round trip left on the dependent chain of a read is the gather of
+// its candidates' counts.  Rows of up to kRowRegs entries take this register path; longer rows take the generic
+// two-pass loop that recomputes the same running sum, bit for bit.
 constexpr int kRowRegs = 12;
 
 struct RowRegs {
     int i;                 // read id (position in the sweep order)
     unsigned len;
     unsigned long long off;
-    int zo;                // current assignment
+    int zo;                // assignment left by the previous sweep
     unsigned raw;          // MT19937 output for this read in this sweep
     int t[kRowRegs];
     double c[kRowRegs];
 };
 
-__device__ __forceinline__ void load_row(const PArgs& a, const int* z, const unsigned* ublk, unsigned long long i0, int q,
-                                         bool use_counts, RowRegs& r) {
+__device__ __forceinline__ void load_row(const PArgs& a, const int* z_prev, const unsigned* u, int q, bool use_counts, RowRegs& r) {
     r.i = a.order[q];
     r.off = a.p_off[q];
     r.len = (unsigned)(a.p_off[q + 1] - r.off);
-    r.zo = use_counts ? ld_cg(z + q) : 0;
-    r.raw = __ldcg(ublk + ((unsigned long long)r.i - i0));
+    r.zo = use_counts ? ld_cg(z_prev + q) : 0;
+    r.raw = __ldcg(u + r.i);
 #pragma unroll
     for (int k = 0; k < kRowRegs; ++k) {
         r.t[k] = k < (int)r.len ? a.p_sid[r.off + k] : 0;
@@ -368,8 +417,8 @@ __device__ __forceinline__ void load_row(const PArgs& a, const int* z, const uns
     }
 }
 
-// returns the new assignment; updates the counts of the component (plain stores: component-private) and counts[0]
-// (atomics: shared by all components).  c0 = snapshot of the noise count.
+// Returns the new assignment and updates the counts of the component (plain stores: component-private).  counts[0] is
+// never touched here: c0 is the noise count this read sees, membership changes are recorded by the caller.
 // The row is processed in chunks of kRowRegs entries: ids / conprb of a chunk with independent loads (the first chunk
 // was prefetched with the row), then the counts and alphas of the chunk with independent gathers, then the
 // left-to-right running sum.  The running sums and the counts seen are kept in a per-thread local array so that the
@@ -432,18 +481,14 @@ __device__ __forceinline__ int draw_row(const PArgs& a, int* counts, const RowRe
         const int znew = l < kRowRegs ? zn_fast : zn;
         if (use_counts) {
             if (znew != zo) {
-                if (zo == 0) atomicSub(counts, 1); else st_cg(counts + zo, cnt_zo);
-                if (znew == 0) atomicAdd(counts, 1); else st_cg(counts + znew, seen[l] + 1);
+                if (zo != 0) st_cg(counts + zo, cnt_zo);
+                if (znew != 0) st_cg(counts + znew, seen[l] + 1);
             }
-        } else {
-            if (znew == 0) atomicAdd(counts, 1); else st_cg(counts + znew, ld_cg(counts + znew) + 1);
-        }
+        } else if (znew != 0) st_cg(counts + znew, ld_cg(counts + znew) + 1);
         return znew;
     }
     // ---- very long rows: generic two-pass loop
-    if (use_counts) {
-        if (zo == 0) atomicSub(counts, 1); else st_cg(counts + zo, ld_cg(counts + zo) - 1);
-    }
+    if (use_counts && zo != 0) st_cg(counts + zo, ld_cg(counts + zo) - 1);
     const int c0_eff = c0 - (use_counts && zo == 0 ? 1 : 0);
     double total = 0.0;
     for (unsigned k = 0; k < r.len; ++k) {
@@ -464,141 +509,165 @@ __device__ __forceinline__ int draw_row(const PArgs& a, int* counts, const RowRe
     }
     if (l < 0) { *err = 3; l = (int)r.len - 1; }
     const int zn = a.p_sid[r.off + l];
-    if (zn == 0) atomicAdd(counts, 1); else st_cg(counts + zn, ld_cg(counts + zn) + 1);
+    if (zn != 0) st_cg(counts + zn, ld_cg(counts + zn) + 1);
     return zn;
 }
 
-// `n` successive outputs of the chain's MT19937 (tempered, raw 32 bit) by one warp
-__device__ void fill_uniforms(MtState& mt, int& mt_idx_s, unsigned* dst, unsigned n, int lane) {
-    int idx = mt_idx_s;
-    unsigned done = 0;
-    while (done < n) {
-        if (idx >= 624) {
-            mt_regenerate(mt, lane);
-            idx = 0;
-        }
-        const unsigned take = min((unsigned)(624 - idx), n - done);
-        for (unsigned k = lane; k < take; k += 32) __stcg(dst + done + k, mt_temper(mt.mt[idx + k]));
-        __syncwarp();
-        idx += (int)take;
-        done += take;
-    }
-    __syncwarp();
-    if (lane == 0) mt_idx_s = idx;
-    __syncwarp();
-}
-
 __global__ void __launch_bounds__(kPThreads) gibbs_parallel_kernel(const PArgs a) {
-    __shared__ MtState mt;
     __shared__ double sh_red[kPThreads / 32];
-    __shared__ int mt_idx_s;
-    const int chain = a.chain_base + blockIdx.x / a.ctas_per_chain;
-    const int cta = blockIdx.x % a.ctas_per_chain;
+    __shared__ int sh_scan[kPThreads];
+    __shared__ int sh_base[512];     // exclusive prefix of the slice totals (<= 512 worker CTAs per chain)
+    const unsigned group = a.ctas_per_chain + 1;   // worker CTAs + the generator CTA
+    const int chain = a.chain_base + blockIdx.x / group;
+    const unsigned cta = blockIdx.x % group;
     const unsigned n_ctas = a.ctas_per_chain;
     const int tid = threadIdx.x;
     const int M1 = a.M + 1;
-    const unsigned chain_threads = n_ctas * kPThreads, ctid = cta * kPThreads + tid;
-    // segment walkers: every thread of the chain except the generator warp (warp 0 of CTA 0)
-    const bool is_gen = cta == 0 && tid < 32;
-    const unsigned n_workers = chain_threads - 32, wid = ctid - 32;
-    unsigned gblock = 0;   // running block number over all sweeps (parity selects the uniform buffer)
-    int* counts = a.counts + (size_t)chain * M1;
-    int* z = a.z + (size_t)chain * a.N1;
-    int* zsave = a.zsave + (size_t)chain * a.block_reads;
+    const unsigned W = a.n_words;
     ChainSync* sy = a.sync + chain;
+    const int n_samples = a.chain_samples[chain];
+    const int chainlen = 1 + (n_samples - 1) * a.gap;
+    const unsigned n_sweeps = 1u + (unsigned)(a.burnin + chainlen);   // sweep 0 = initial state from conprb alone
+    unsigned* ubuf = a.ubuf + (size_t)chain * 2 * a.N1;
+    if (cta == n_ctas) {
+        generator_loop(a, sy, ubuf, n_sweeps, a.chain_seeds[chain]);
+        return;
+    }
+    const unsigned chain_threads = n_ctas * kPThreads, ctid = cta * kPThreads + tid;
+    int* counts = a.counts + (size_t)chain * M1;
+    int* counts_start = a.counts_start + (size_t)chain * M1;
+    int* zbuf = a.z + (size_t)chain * 2 * a.N1;
+    unsigned* fl = a.flips + (size_t)chain * 4 * W;
+    int* pre = a.pre + (size_t)chain * W;
+    int* slice_tot = a.slice_tot + (size_t)chain * n_ctas;
     double* acc = a.acc + (size_t)chain * (4 * (size_t)M1 + a.n_genes);
     double* theta = a.theta_tmp + (size_t)chain * 2 * M1;
     double* fpkm = theta + M1;
-    const int n_samples = a.chain_samples[chain];
     int* cv = a.count_vectors + a.chain_cv_offset[chain] * M1;
+    // this CTA's slice of flip words (prefix sums are formed per slice, the slice bases are added on the fly)
+    const unsigned w_per = (W + n_ctas - 1) / n_ctas;
+    const unsigned w_lo = min(W, cta * w_per), w_hi = min(W, w_lo + w_per);
 
     for (int i = ctid; i < M1; i += chain_threads) st_cg(counts + i, a.init_counts[i] + (i == 0 ? (int)a.n0 : 0));
-    if (cta == 0 && tid == 0) {
-        mt.mt[0] = a.chain_seeds[chain];
-        for (int k = 1; k < 624; ++k) mt.mt[k] = 1812433253u * (mt.mt[k - 1] ^ (mt.mt[k - 1] >> 30)) + (unsigned)k;
-        mt_idx_s = 624;
-    }
     chain_barrier(sy, n_ctas);
 
-    const int chainlen = 1 + (n_samples - 1) * a.gap;
     int kept = 0;
-    unsigned flip_parity = 0;
-    for (int round = 0; round <= a.burnin + chainlen; ++round) {   // round 0 = initial state from conprb alone
-        const bool use_counts = round > 0;
-        for (int b = 0; b < a.n_blocks; ++b) {
-            const unsigned long long i0 = (unsigned long long)b * a.block_reads;
-            const unsigned nb = (unsigned)min((unsigned long long)a.block_reads, a.N1 - i0);
-            // ---- uniforms of this block (warp 0 of CTA 0: warp-synchronous regeneration is several times faster than a
-            //      CTA-wide one, whose __syncthreads dominate) and a copy of z for roll-backs (everyone else meanwhile)
-            long long tk0 = clock64();
-            // uniforms: warp 0 of CTA 0 is the chain's generator and runs one block ahead of the workers (the very
-            // first block is produced here, every later one during the previous block's first pass)
-            unsigned* ucur = a.ublk + ((size_t)chain * 2 + (gblock & 1u)) * a.block_reads;
-            unsigned* unext = a.ublk + ((size_t)chain * 2 + ((gblock + 1u) & 1u)) * a.block_reads;
-            if (gblock == 0 && cta == 0 && tid < 32) fill_uniforms(mt, mt_idx_s, ucur, nb, tid);
-            if (use_counts)
-                for (unsigned k = ctid; k < nb; k += chain_threads) st_cg(zsave + k, ld_cg(z + i0 + k));  // slot order
-            if (cta == 0 && tid == 0) { sy->flip[0] = 0xffffffffu; sy->flip[1] = 0xffffffffu; }
-            long long tk1 = clock64();
-            chain_barrier(sy, n_ctas);
-            long long tk2 = clock64();
-            if (cta == 0 && tid == 0) { sy->prof[0] += tk1 - tk0; sy->prof[1] += tk2 - tk1; }
-
-            unsigned long long lo = i0;   // first position that still has to be (re)drawn
-            const int s0 = a.blk_seg[b], s1 = a.blk_seg[b + 1];
-            for (;;) {
-                const int c0 = ld_cg(counts);   // snapshot of the noise count, valid for every position >= lo
-                unsigned* flip = &sy->flip[flip_parity];
-                const long long tp0 = clock64();
-                if (is_gen) {   // next block's uniforms, once per block (not on redo passes)
-                    if (lo == i0) {
-                        const bool last = round == a.burnin + chainlen && b == a.n_blocks - 1;
-                        if (!last) {
-                            const int bn = b + 1 < a.n_blocks ? b + 1 : 0;
-                            const unsigned long long in0 = (unsigned long long)bn * a.block_reads;
-                            fill_uniforms(mt, mt_idx_s, unext, (unsigned)min((unsigned long long)a.block_reads, a.N1 - in0), tid);
-                        }
-                    }
-                } else
-                for (int sgm = s0 + (int)wid; sgm < s1; sgm += (int)n_workers) {
-                    const int q_end = a.seg_start[sgm + 1];
-                    int q = a.seg_start[sgm];
-                    RowRegs nxt;
-                    load_row(a, z, ucur, i0, q, use_counts, nxt);
-                    for (; q < q_end; ++q) {
-                        const RowRegs cur = nxt;
-                        if (q + 1 < q_end) load_row(a, z, ucur, i0, q + 1, use_counts, nxt);   // in flight while `cur` is drawn
-                        if ((unsigned long long)cur.i < lo) continue;
-                        const int zn = draw_row(a, counts, cur, use_counts, c0, &sy->err);
-                        st_cg(z + q, zn);
-                        if (use_counts && ((cur.zo == 0) != (zn == 0))) atomicMin(flip, (unsigned)((unsigned long long)cur.i - i0));
-                    }
-                }
-                const long long tp1 = clock64();
+    for (unsigned sweep = 0; sweep < n_sweeps; ++sweep) {
+        const bool use_counts = sweep > 0;
+        const int round = (int)sweep;
+        const unsigned* u = ubuf + (size_t)(sweep & 1u) * a.N1;
+        const int* z_prev = zbuf + (size_t)((sweep + 1u) & 1u) * a.N1;
+        int* z_cur = zbuf + (size_t)(sweep & 1u) * a.N1;
+        long long t0 = clock64();
+        if (tid == 0) {
+            while (*((volatile unsigned*)&sy->u_ready) < sweep + 1) {}
+            __threadfence();
+        }
+        __syncthreads();
+        long long t1 = clock64();
+        if (cta == 0 && tid == 0) sy->prof[0] += t1 - t0;
+        const int c0_start = ld_cg(counts);
+        // start of the sweep: copy of the counts for restarts; the input flip set (set 0) is empty
+        if (use_counts) {
+            for (int i = ctid; i < M1; i += chain_threads) st_cg(counts_start + i, ld_cg(counts + i));
+            for (unsigned w = ctid; w < 2 * W; w += chain_threads) __stcg(fl + w, 0u);
+            for (unsigned w = w_lo + tid; w < w_hi; w += kPThreads) st_cg(pre + w, 0);
+            if (tid == 0) st_cg(slice_tot + cta, 0);
+        }
+        unsigned in_set = 0;   // flip set the pass reads; it writes the other one
+        for (unsigned pass = 0;; ++pass) {
+            unsigned* f_in = fl + (size_t)in_set * 2 * W;
+            unsigned* f_out = fl + (size_t)(in_set ^ 1u) * 2 * W;
+            if (use_counts) {
+                for (unsigned w = ctid; w < 2 * W; w += chain_threads) __stcg(f_out + w, 0u);
+                if (pass > 0)
+                    for (int i = ctid + 1; i < M1; i += chain_threads) st_cg(counts + i, ld_cg(counts_start + i));
+                if (cta == 0 && tid == 0) { sy->changed = 0; sy->passes++; }
                 chain_barrier(sy, n_ctas);
-                if (cta == 0 && tid == 0) { sy->prof[2] += tp1 - tp0; sy->prof[3] += clock64() - tp1; }
-                const unsigned p = *((volatile unsigned*)flip);
-                if (p == 0xffffffffu) break;
-                // ---- roll back everything after position p of the block, then redo it with the corrected c0
-                const unsigned long long redo = i0 + p + 1;
-                if (!is_gen)
-                for (int sgm = s0 + (int)wid; sgm < s1; sgm += (int)n_workers) {
-                    for (int q = a.seg_start[sgm]; q < a.seg_start[sgm + 1]; ++q) {
-                        const unsigned long long i = (unsigned long long)a.order[q];
-                        if (i < redo || i < lo) continue;
-                        const int zn = ld_cg(z + q), zo = ld_cg(zsave + ((unsigned long long)q - i0));
-                        if (zn == 0) atomicSub(counts, 1); else st_cg(counts + zn, ld_cg(counts + zn) - 1);
-                        if (zo == 0) atomicAdd(counts, 1); else st_cg(counts + zo, ld_cg(counts + zo) + 1);
-                        st_cg(z + q, zo);
-                    }
+                // exclusive prefix of the slice totals of the input set
+                for (unsigned c = tid; c < n_ctas; c += kPThreads) sh_base[c] = ld_cg(slice_tot + c);
+                __syncthreads();
+                if (tid == 0) {
+                    int run = 0;
+                    for (unsigned c = 0; c < n_ctas; ++c) { const int v = sh_base[c]; sh_base[c] = run; run += v; }
                 }
-                if (cta == 0 && tid == 0) sy->flip[flip_parity ^ 1u] = 0xffffffffu;
-                flip_parity ^= 1u;
-                lo = redo;
-                chain_barrier(sy, n_ctas);
-                if (lo >= i0 + nb) break;
+                __syncthreads();
             }
-            ++gblock;
+            const long long tp0 = clock64();
+            for (int sgm = (int)ctid; sgm < a.n_segs; sgm += (int)chain_threads) {
+                const int q_end = a.seg_start[sgm + 1];
+                int q = a.seg_start[sgm];
+                RowRegs nxt;
+                load_row(a, z_prev, u, q, use_counts, nxt);
+                for (; q < q_end; ++q) {
+                    const RowRegs cur = nxt;
+                    if (q + 1 < q_end) load_row(a, z_prev, u, q + 1, use_counts, nxt);   // in flight while `cur` is drawn
+                    int c0 = c0_start;
+                    if (use_counts) {   // noise count seen by read i: flips of the input set before position i
+                        const unsigned w = (unsigned)cur.i >> 5, m = (1u << ((unsigned)cur.i & 31u)) - 1u;
+                        c0 += sh_base[w / w_per] + ld_cg(pre + w) + __popc(__ldcg(f_in + w) & m) - __popc(__ldcg(f_in + W + w) & m);
+                    }
+                    const int zn = draw_row(a, counts, cur, use_counts, c0, &sy->err);
+                    st_cg(z_cur + q, zn);
+                    if (use_counts) {
+                        if (cur.zo != 0 && zn == 0) atomicOr(f_out + ((unsigned)cur.i >> 5), 1u << ((unsigned)cur.i & 31u));
+                        if (cur.zo == 0 && zn != 0) atomicOr(f_out + W + ((unsigned)cur.i >> 5), 1u << ((unsigned)cur.i & 31u));
+                    } else if (zn == 0) atomicAdd(counts, 1);
+                }
+            }
+            const long long tp1 = clock64();
+            if (cta == 0 && tid == 0) sy->prof[1] += tp1 - tp0;
+            if (!use_counts) {
+                chain_barrier(sy, n_ctas);
+                break;
+            }
+            chain_barrier(sy, n_ctas);
+            // compare the two sets on this CTA's slice and form the prefix sums of the output set
+            bool diff = false;
+            int part = 0;
+            const unsigned per_thread = (w_hi - w_lo + kPThreads - 1) / kPThreads;
+            const unsigned my_lo = min(w_hi, w_lo + tid * per_thread), my_hi = min(w_hi, my_lo + per_thread);
+            for (unsigned w = my_lo; w < my_hi; ++w) {
+                const unsigned pj = __ldcg(f_out + w), pl = __ldcg(f_out + W + w);
+                diff = diff || pj != __ldcg(f_in + w) || pl != __ldcg(f_in + W + w);
+                part += __popc(pj) - __popc(pl);
+            }
+            sh_scan[tid] = part;
+            __syncthreads();
+            if (tid == 0) {
+                int run = 0;
+                for (int t = 0; t < kPThreads; ++t) { const int v = sh_scan[t]; sh_scan[t] = run; run += v; }
+                st_cg(slice_tot + cta, run);
+            }
+            __syncthreads();
+            {
+                int run = sh_scan[tid];
+                for (unsigned w = my_lo; w < my_hi; ++w) {
+                    st_cg(pre + w, run);
+                    run += __popc(__ldcg(f_out + w)) - __popc(__ldcg(f_out + W + w));
+                }
+            }
+            if (__syncthreads_or(diff) && tid == 0) atomicExch(&sy->changed, 1u);
+            chain_barrier(sy, n_ctas);
+            in_set ^= 1u;   // the output set (with its prefix sums) is the next pass's input - or the final flip set
+            if (*((volatile unsigned*)&sy->changed) == 0) break;
+            chain_barrier(sy, n_ctas);   // everyone has read `changed` before CTA 0 clears it
+        }
+        if (use_counts) {
+            // net change of the noise count = all flips of the final set
+            for (unsigned c = tid; c < n_ctas; c += kPThreads) sh_base[c] = ld_cg(slice_tot + c);
+            __syncthreads();
+            if (cta == 0 && tid == 0) {
+                int run = 0;
+                for (unsigned c = 0; c < n_ctas; ++c) run += sh_base[c];
+                st_cg(counts, c0_start + run);
+            }
+        }
+        const long long t2 = clock64();
+        chain_barrier(sy, n_ctas);
+        if (cta == 0 && tid == 0) {
+            __threadfence();
+            atomicExch(&sy->sweeps_done, sweep + 1);   // this sweep's uniforms (and the previous z) are no longer read
         }
         if (round > a.burnin && (round - a.burnin - 1) % a.gap == 0) {   // Gibbs.cpp:313-346, by CTA 0 of the chain
             if (cta == 0) {
@@ -645,6 +714,7 @@ __global__ void __launch_bounds__(kPThreads) gibbs_parallel_kernel(const PArgs a
             ++kept;
             chain_barrier(sy, n_ctas);
         }
+        if (cta == 0 && tid == 0) { sy->prof[2] += t2 - t1; sy->prof[3] += clock64() - t2; }
     }
 }
 
@@ -790,35 +860,33 @@ int gibbs_prepare(rsem_b200_ctx* c, const uint64_t* row_ptr, const int32_t* sid)
         }
     }
     g.max_len = (uint32_t)max_len;
-    // component key of a read: root of its first non-noise transcript; reads with only the noise entry get a unique key
-    std::vector<int64_t> key(N1);
+    // component of a read = root of its first non-noise transcript; 0 = the row holds only the noise entry (its own segment)
+    std::vector<int32_t> comp(N1);
+    std::vector<uint32_t> comp_reads((size_t)M + 1, 0);
+    uint64_t n_lonely = 0;
     for (uint64_t i = 0; i < N1; ++i) {
-        int64_t k = -(int64_t)i - 1;
+        int32_t k = 0;
         for (uint64_t j = row_ptr[i]; j < row_ptr[i + 1]; ++j)
             if (sid[j] != 0) { k = find(sid[j]); break; }
-        key[i] = k;
+        comp[i] = k;
+        if (k) ++comp_reads[k]; else ++n_lonely;
     }
-    int B = 16384;
-    if (const char* e = getenv("RSEM_B200_GIBBS_BLOCK")) { const int v = atoi(e); if (v >= 32) B = v; }
-    const int n_blocks = (int)((N1 + B - 1) / B);
-    std::vector<int32_t> order(N1), seg_start, blk_seg(n_blocks + 1);
-    seg_start.reserve(N1 / 4 + 16);
-    std::vector<int32_t> idx;
-    for (int b = 0; b < n_blocks; ++b) {
-        const uint64_t i0 = (uint64_t)b * B, i1 = std::min<uint64_t>(N1, i0 + B);
-        idx.resize(i1 - i0);
-        for (uint64_t i = i0; i < i1; ++i) idx[i - i0] = (int32_t)i;
-        std::stable_sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return key[x] < key[y]; });
-        blk_seg[b] = (int32_t)seg_start.size();
-        for (uint64_t q = 0; q < idx.size(); ++q) {
-            if (q == 0 || key[idx[q]] != key[idx[q - 1]]) seg_start.push_back((int32_t)(i0 + q));
-            order[i0 + q] = idx[q];
-        }
+    // segments: one per component, longest first (a thread walks a whole segment: the long ones must start first),
+    // then the noise-only reads one by one; reads keep their order inside a segment (counting sort)
+    std::vector<int32_t> roots;
+    for (int t = 1; t <= M; ++t) if (comp_reads[t]) roots.push_back(t);
+    std::stable_sort(roots.begin(), roots.end(), [&](int32_t x, int32_t y) { return comp_reads[x] > comp_reads[y]; });
+    std::vector<int32_t> seg_start;
+    seg_start.reserve(roots.size() + n_lonely + 1);
+    std::vector<uint64_t> fill((size_t)M + 1, 0);
+    uint64_t at = 0;
+    for (int32_t r : roots) { seg_start.push_back((int32_t)at); fill[r] = at; at += comp_reads[r]; }
+    std::vector<int32_t> order(N1);
+    for (uint64_t i = 0; i < N1; ++i) {
+        if (comp[i]) order[fill[comp[i]]++] = (int32_t)i;
+        else { seg_start.push_back((int32_t)at); order[at++] = (int32_t)i; }
     }
-    blk_seg[n_blocks] = (int32_t)seg_start.size();
     seg_start.push_back((int32_t)N1);
-    g.block_reads = B;
-    g.n_blocks = n_blocks;
     g.n_segs = (int32_t)seg_start.size() - 1;
     // rows re-laid in slot order so that a segment is one contiguous stream
     {
@@ -846,9 +914,7 @@ int gibbs_prepare(rsem_b200_ctx* c, const uint64_t* row_ptr, const int32_t* sid)
         RB_CUDA(cudaStreamSynchronize(c->stream));
     }
     RB_CUDA(cudaMalloc(&g.seg_start, seg_start.size() * sizeof(int32_t)));
-    RB_CUDA(cudaMalloc(&g.blk_seg, blk_seg.size() * sizeof(int32_t)));
     RB_CUDA(cudaMemcpyAsync(g.seg_start, seg_start.data(), seg_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    RB_CUDA(cudaMemcpyAsync(g.blk_seg, blk_seg.data(), blk_seg.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -860,26 +926,37 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
     std::vector<long long> cv_off(nc);
     for (int t = 0; t < nc; ++t) { cv_off[t] = total_samples; total_samples += p->chain_samples[t]; }
     const size_t acc_per = 4 * (size_t)M1 + p->n_genes;
+    const unsigned W = (unsigned)((g.N1 + 31) / 32);
 
     PArgs a{};
     a.N1 = g.N1;
-    a.row_ptr = reinterpret_cast<const unsigned long long*>(g.row_ptr);
-    a.sid = g.sid; a.conprb = g.conprb; a.order = g.order; a.seg_start = g.seg_start; a.blk_seg = g.blk_seg;
+    a.order = g.order; a.seg_start = g.seg_start; a.n_segs = g.n_segs;
     a.p_off = reinterpret_cast<const unsigned long long*>(g.p_off); a.p_sid = g.p_sid; a.p_con = g.p_con;
-    a.block_reads = g.block_reads; a.n_blocks = g.n_blocks;
     a.M = p->M; a.burnin = p->burnin; a.gap = p->gap; a.n_genes = p->n_genes; a.n_chains = nc;
     a.n0 = p->n0; a.totc = p->totc;
+    a.n_words = W;
 
-    int *d_samples = nullptr, *d_init = nullptr, *d_gene = nullptr, *d_counts = nullptr, *d_z = nullptr, *d_cv = nullptr, *d_zsave = nullptr;
-    unsigned *d_seeds = nullptr, *d_u = nullptr;
+    // co-resident CTAs: chains run in waves, every chain gets the same number of worker CTAs (one thread per component
+    // is all the parallelism a sweep has) + 1 generator CTA
+    int per_sm = 0;
+    RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_parallel_kernel, kPThreads, 0));
+    const int resident = std::max(1, per_sm) * c->sm_count;
+    int ctas = std::max(1, std::min(512, (g.n_segs + kPThreads - 1) / kPThreads));
+    if (const char* e = getenv("RSEM_B200_GIBBS_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 512) ctas = v; }
+    ctas = std::min(ctas, std::max(1, resident / std::min(nc, std::max(1, resident / 2)) - 1));
+    const int chains_per_wave = std::max(1, std::min(nc, resident / (ctas + 1)));
+
+    int *d_samples = nullptr, *d_init = nullptr, *d_gene = nullptr, *d_counts = nullptr, *d_counts0 = nullptr, *d_z = nullptr, *d_cv = nullptr,
+        *d_pre = nullptr, *d_tot = nullptr;
+    unsigned *d_seeds = nullptr, *d_u = nullptr, *d_flips = nullptr;
     long long* d_off = nullptr;
     ChainSync* d_sync = nullptr;
     double *d_alpha = nullptr, *d_eel = nullptr, *d_mw = nullptr, *d_acc = nullptr, *d_tmp = nullptr;
     int rc = 0;
     auto cleanup = [&]() {
-        cudaFree(d_samples); cudaFree(d_init); cudaFree(d_gene); cudaFree(d_counts); cudaFree(d_z); cudaFree(d_cv); cudaFree(d_zsave);
-        cudaFree(d_seeds); cudaFree(d_u); cudaFree(d_off); cudaFree(d_sync); cudaFree(d_alpha); cudaFree(d_eel); cudaFree(d_mw);
-        cudaFree(d_acc); cudaFree(d_tmp);
+        cudaFree(d_samples); cudaFree(d_init); cudaFree(d_gene); cudaFree(d_counts); cudaFree(d_counts0); cudaFree(d_z); cudaFree(d_cv);
+        cudaFree(d_pre); cudaFree(d_tot); cudaFree(d_seeds); cudaFree(d_u); cudaFree(d_flips); cudaFree(d_off); cudaFree(d_sync);
+        cudaFree(d_alpha); cudaFree(d_eel); cudaFree(d_mw); cudaFree(d_acc); cudaFree(d_tmp);
     };
 #define RB_TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
 #define RB_TRYC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #x, __FILE__, __LINE__); } } while (0)
@@ -892,34 +969,31 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
     RB_TRY(to_dev(&d_mw, p->mw, M1, c->stream));
     RB_TRY(to_dev(&d_gene, p->gene_start, (size_t)p->n_genes + 1, c->stream));
     RB_TRYC(cudaMalloc(&d_counts, (size_t)nc * M1 * sizeof(int)));
-    RB_TRYC(cudaMalloc(&d_z, std::max<size_t>((size_t)nc * g.N1, 1) * sizeof(int)));
-    RB_TRYC(cudaMalloc(&d_zsave, (size_t)nc * g.block_reads * sizeof(int)));
-    RB_TRYC(cudaMalloc(&d_u, (size_t)nc * 2 * g.block_reads * sizeof(unsigned)));
+    RB_TRYC(cudaMalloc(&d_counts0, (size_t)nc * M1 * sizeof(int)));
+    RB_TRYC(cudaMalloc(&d_z, (size_t)nc * 2 * g.N1 * sizeof(int)));
+    RB_TRYC(cudaMalloc(&d_u, (size_t)nc * 2 * g.N1 * sizeof(unsigned)));
+    RB_TRYC(cudaMalloc(&d_flips, (size_t)nc * 4 * W * sizeof(unsigned)));
+    RB_TRYC(cudaMalloc(&d_pre, (size_t)nc * W * sizeof(int)));
+    RB_TRYC(cudaMalloc(&d_tot, (size_t)nc * ctas * sizeof(int)));
     RB_TRYC(cudaMalloc(&d_sync, (size_t)nc * sizeof(ChainSync)));
     RB_TRYC(cudaMalloc(&d_cv, std::max<size_t>((size_t)total_samples * M1, 1) * sizeof(int)));
     RB_TRYC(cudaMalloc(&d_acc, (size_t)nc * acc_per * sizeof(double)));
     RB_TRYC(cudaMalloc(&d_tmp, (size_t)nc * 2 * M1 * sizeof(double)));
     RB_TRYC(cudaMemsetAsync(d_acc, 0, (size_t)nc * acc_per * sizeof(double), c->stream));
     RB_TRYC(cudaMemsetAsync(d_sync, 0, (size_t)nc * sizeof(ChainSync), c->stream));
+    RB_TRYC(cudaMemsetAsync(d_tot, 0, (size_t)nc * ctas * sizeof(int), c->stream));
     a.chain_samples = d_samples; a.chain_seeds = d_seeds; a.chain_cv_offset = d_off; a.init_counts = d_init;
-    a.alpha = d_alpha; a.eel = d_eel; a.mw = d_mw; a.gene_start = d_gene; a.counts = d_counts; a.z = d_z;
-    a.zsave = d_zsave; a.ublk = d_u; a.sync = d_sync; a.count_vectors = d_cv; a.acc = d_acc; a.theta_tmp = d_tmp;
+    a.alpha = d_alpha; a.eel = d_eel; a.mw = d_mw; a.gene_start = d_gene; a.counts = d_counts; a.counts_start = d_counts0; a.z = d_z;
+    a.ubuf = d_u; a.flips = d_flips; a.pre = d_pre; a.slice_tot = d_tot; a.sync = d_sync; a.count_vectors = d_cv; a.acc = d_acc;
+    a.theta_tmp = d_tmp;
 
-    // co-resident CTAs: chains are run in waves of at most sm_count, every chain gets the same number of CTAs
-    int per_sm = 0;
-    RB_TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_parallel_kernel, kPThreads, 0));
-    const int resident = std::max(1, per_sm) * c->sm_count;
-    const double segs_per_block = (double)g.n_segs / std::max(1, g.n_blocks);
-    for (int base = 0; base < nc;) {
-        const int wave = std::min(nc - base, resident);
-        int ctas = std::max(1, std::min(resident / wave, (int)(segs_per_block / kPThreads) + 1));
-        if (const char* e = getenv("RSEM_B200_GIBBS_CTAS")) { const int v = atoi(e); if (v >= 1 && v * wave <= resident) ctas = v; }
+    for (int base = 0; base < nc; base += chains_per_wave) {
+        const int wave = std::min(nc - base, chains_per_wave);
         a.chain_base = base;
         a.ctas_per_chain = ctas;
         void* kargs[] = {(void*)&a};
-        RB_TRYC(cudaLaunchCooperativeKernel((void*)gibbs_parallel_kernel, dim3(wave * ctas), dim3(kPThreads), kargs, 0, c->stream));
+        RB_TRYC(cudaLaunchCooperativeKernel((void*)gibbs_parallel_kernel, dim3(wave * (ctas + 1)), dim3(kPThreads), kargs, 0, c->stream));
         c->launches++;
-        base += wave;
     }
     std::vector<double> h_acc((size_t)nc * acc_per);
     std::vector<ChainSync> h_sync(nc);
@@ -931,8 +1005,9 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
 #undef RB_TRY
 #undef RB_TRYC
     if (getenv("RSEM_B200_TIMING"))
-        fprintf(stderr, "gibbs chain 0, CTA 0 thread 0 cycles: rng %llu, copy %llu(incl. barrier wait), pass %llu, pass-barrier wait %llu\n",
-                h_sync[0].prof[0], h_sync[0].prof[1], h_sync[0].prof[2], h_sync[0].prof[3]);
+        fprintf(stderr, "gibbs chain 0 (%d worker CTAs, %d segments): %u passes; worker CTA 0 thread 0 cycles: wait for uniforms %llu, passes %llu, "
+                "barriers + bookkeeping %llu (incl. the passes), per-sample work %llu\n", ctas, g.n_segs, h_sync[0].passes, h_sync[0].prof[0],
+                h_sync[0].prof[1], h_sync[0].prof[2], h_sync[0].prof[3]);
     for (int t = 0; t < nc; ++t)
         if (h_sync[t].err) {
             set_error("gibbs: categorical draw fell off the cumulative array (reference: assert(l < len), sampling.h:62)");
@@ -956,7 +1031,8 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
 int gibbs_run(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p, rsem_b200_gibbs_out* out) {
     const char* mode = getenv("RSEM_B200_GIBBS");   // "serial" = the one-warp-per-chain kernel (cross-check / debugging)
     if (mode && !strcmp(mode, "serial")) return gibbs_run_serial(c, p, out);
-    if (c->gibbs.N1 == 0 || !c->gibbs.order) return gibbs_run_serial(c, p, out);
+    // tiny inputs: a 624-word regeneration would span more than two sweeps (the generator runs only one sweep ahead)
+    if (c->gibbs.N1 < 1248 || !c->gibbs.order) return gibbs_run_serial(c, p, out);
     return gibbs_run_parallel(c, p, out);
 }
 

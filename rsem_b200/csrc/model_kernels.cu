@@ -61,6 +61,8 @@ struct ModelArgs {
     int prof_rows_smem;     // rows of the profile table staged in shared memory (0 = use global)
     int q_rows;             // quality models: (largest quality value in the read set) + 1
     int* err_flag;
+    const unsigned char* uni;   // per read: 1 = every hit sees the same bases in read direction (window_uniform_kernel)
+    int mode;                   // 0: every read on the per-hit path, 1: only uniform reads (cooperative path), 2: only the others
 };
 
 __device__ __forceinline__ double ld_adj(const DevLenDist& d, int len, int refL) {
@@ -226,8 +228,76 @@ __device__ __forceinline__ double noise_prob(const ModelArgs& a, const double* n
     return prob;
 }
 
-template <bool HASQ>
-__device__ double conprb_single(const ModelArgs& a, const double* prof, unsigned long long i, int s, int pos) {
+// ---- cooperative products for "uniform" reads ------------------------------------------------------------------------
+// When all hits of a read show it the same bases (reads inside exons shared by the isoforms of a gene - the common case),
+// the product over its bases is the same for every hit: the G lanes of the read's group each take a contiguous range of
+// 8-base chunks and the partial products are multiplied in a butterfly (every lane ends with the same bits: fp
+// multiplication is commutative and the tree is symmetric).  The product is therefore associated differently from the
+// reference's left-to-right loop (SingleQModel.h:127-137): relative difference <= a few 1e-14, far inside the 1e-6 the
+// outputs are compared at; non-uniform reads keep the reference's order.
+template <int G>
+__device__ __forceinline__ double group_product(double v) {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int G, bool HASQ>
+__device__ __forceinline__ double seq_prob_coop(const ModelArgs& a, const double* prof, int mate, unsigned long long i, int sid,
+                                                int pos, int dir, int g, bool active) {
+    const unsigned long long o = a.roff[mate][i];
+    const int len = (int)(a.roff[mate][i + 1] - o);
+    const int totLen = a.tot_len[sid];
+    const int n_chunks = (len + 7) >> 3;
+    const int c0 = g * n_chunks / G, c1 = (g + 1) * n_chunks / G;
+    double prob = 1.0;
+    if (active && c1 > c0) {
+        FwdBytes rb(a.rbase[mate] + o + 8 * c0);
+        FwdBytes rq(HASQ ? a.rqual[mate] + o + 8 * c0 : a.rbase[mate] + o, HASQ);
+        const unsigned char* s0 = a.seq + a.seq_off[sid] + (dir == 0 ? pos + 8 * c0 : totLen - 1 - pos - 8 * c0);
+        RefStream sb(s0, dir != 0, a.seq, true);
+        for (int c = c0; c < c1; ++c) {
+            const bool more = c + 1 < c1;
+            const unsigned long long ws = sb.next(more), wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
+            const int k0 = 8 * c, n = min(8, len - k0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < n) {
+                    const int row = HASQ ? (int)byte_of(wq, k) : k0 + k;
+                    prob *= prof[(row * 5 + sb.base_at(ws, k)) * 5 + (int)byte_of(wr, k)];
+                }
+            }
+        }
+    }
+    return group_product<G>(prob);
+}
+
+template <int G, bool HASQ>
+__device__ __forceinline__ double noise_prob_coop(const ModelArgs& a, const double* nprof, int mate, unsigned long long i, int g,
+                                                  bool active) {
+    const unsigned long long o = a.roff[mate][i];
+    const int len = (int)(a.roff[mate][i + 1] - o);
+    const int n_chunks = (len + 7) >> 3;
+    const int c0 = g * n_chunks / G, c1 = (g + 1) * n_chunks / G;
+    double prob = 1.0;
+    if (active && c1 > c0) {
+        FwdBytes rb(a.rbase[mate] + o + 8 * c0);
+        FwdBytes rq(HASQ ? a.rqual[mate] + o + 8 * c0 : a.rbase[mate] + o, HASQ);
+        for (int c = c0; c < c1; ++c) {
+            const bool more = c + 1 < c1;
+            const unsigned long long wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
+            const int n = min(8, len - 8 * c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < n) prob *= HASQ ? nprof[byte_of(wq, k) * 5 + byte_of(wr, k)] : nprof[byte_of(wr, k)];
+        }
+    }
+    return group_product<G>(prob);
+}
+
+// COOP: the products over the bases (S1, S2) were formed cooperatively and are passed in
+template <bool HASQ, bool COOP = false>
+__device__ double conprb_single(const ModelArgs& a, const double* prof, unsigned long long i, int s, int pos, double S1 = 1.0) {
     const DevModel& m = a.m;
     const int sid = abs(s), dir = s < 0;
     const int fullLen = a.full_len[sid], totLen = a.tot_len[sid];
@@ -249,15 +319,15 @@ __device__ double conprb_single(const ModelArgs& a, const double* prof, unsigned
         const int effL = min(fullLen, totLen - readLen + 1);
         value = ld_adj(m.gld, readLen, totLen) * rspd_adj(m, fpos, effL, fullLen);
     }
-    double prob = m.ori[dir] * value * seq_prob<HASQ>(a, prof, 0, i, sid, pos, dir);
+    double prob = m.ori[dir] * value * (COOP ? S1 : seq_prob<HASQ>(a, prof, 0, i, sid, pos, dir));
     if (prob < kEpsilon) prob = 0.0;
     const double w = m.mw[sid];
     return w < kEpsilon ? 0.0 : prob / w;
 }
 
-template <bool HASQ>
+template <bool HASQ, bool COOP = false>
 __device__ double conprb_paired(const ModelArgs& a, const double* prof, unsigned long long i, int s, int pos,
-                                int insertLen) {
+                                int insertLen, double S1 = 1.0, double S2 = 1.0) {
     const DevModel& m = a.m;
     const int sid = abs(s), dir = s < 0;
     const int fullLen = a.full_len[sid], totLen = a.tot_len[sid];
@@ -267,25 +337,25 @@ __device__ double conprb_paired(const ModelArgs& a, const double* prof, unsigned
     if (fpos >= fullLen || ref_mask(a, sid, fpos)) return 0.0;
     double prob = m.ori[dir] * ld_adj(m.gld, insertLen, totLen) * rspd_adj(m, fpos, effL, fullLen);
     const int len1 = (int)(a.roff[0][i + 1] - a.roff[0][i]), len2 = (int)(a.roff[1][i + 1] - a.roff[1][i]);
-    prob *= ld_adj(m.mld, len1, insertLen) * seq_prob<HASQ>(a, prof, 0, i, sid, pos, dir);
-    prob *= ld_adj(m.mld, len2, insertLen) * seq_prob<HASQ>(a, prof, 1, i, sid, totLen - pos - insertLen, !dir);
+    prob *= ld_adj(m.mld, len1, insertLen) * (COOP ? S1 : seq_prob<HASQ>(a, prof, 0, i, sid, pos, dir));
+    prob *= ld_adj(m.mld, len2, insertLen) * (COOP ? S2 : seq_prob<HASQ>(a, prof, 1, i, sid, totLen - pos - insertLen, !dir));
     if (prob < kEpsilon) prob = 0.0;
     const double w = m.mw[sid];
     return w < kEpsilon ? 0.0 : prob / w;
 }
 
-template <bool HASQ>
-__device__ double noise_conprb(const ModelArgs& a, const double* nprof, unsigned long long i) {
+template <bool HASQ, bool COOP = false>
+__device__ double noise_conprb(const ModelArgs& a, const double* nprof, unsigned long long i, double P1 = 1.0, double P2 = 1.0) {
     const DevModel& m = a.m;
     double prob;
     if (m.model_type < 2) {
         const int readLen = (int)(a.roff[0][i + 1] - a.roff[0][i]);
         prob = m.has_mld ? ld_prob(m.mld, readLen) : ld_prob(m.gld, readLen);
-        prob *= noise_prob<HASQ>(a, nprof, 0, i);
+        prob *= COOP ? P1 : noise_prob<HASQ>(a, nprof, 0, i);
     } else {
         const int len1 = (int)(a.roff[0][i + 1] - a.roff[0][i]), len2 = (int)(a.roff[1][i + 1] - a.roff[1][i]);
-        prob = ld_prob(m.mld, len1) * noise_prob<HASQ>(a, nprof, 0, i);
-        prob *= ld_prob(m.mld, len2) * noise_prob<HASQ>(a, nprof, 1, i);
+        prob = ld_prob(m.mld, len1) * (COOP ? P1 : noise_prob<HASQ>(a, nprof, 0, i));
+        prob *= ld_prob(m.mld, len2) * (COOP ? P2 : noise_prob<HASQ>(a, nprof, 1, i));
     }
     if (prob < kEpsilon) prob = 0.0;
     const double w = m.mw[0];
@@ -312,7 +382,44 @@ __global__ void __launch_bounds__(kBlock) conprb_kernel(const ModelArgs a) {
     }
     const int lane = threadIdx.x & 31, g = lane % G;
     const unsigned long long groups_total = (unsigned long long)gridDim.x * (kBlock / G);
+    if (a.mode == 1) {
+        // cooperative path: reads whose hits all show them the same bases (a.uni); whole warps stay convergent
+        const unsigned long long base0 = (unsigned long long)blockIdx.x * (kBlock / G) + threadIdx.x / G;
+        const unsigned long long n_iter = (a.N + groups_total - 1) / groups_total;
+        for (unsigned long long it = 0; it < n_iter; ++it) {
+            const unsigned long long i = base0 + it * groups_total;
+            const bool in = i < a.N;
+            const bool lq = in && a.lowq[i] != 0;
+            const bool act = in && a.uni[i] != 0;
+            unsigned long long fr = 0, to = 0;
+            if (act) { fr = a.row_ptr[i]; to = a.row_ptr[i + 1]; }
+            if (__ballot_sync(0xffffffffu, act) == 0u) continue;
+            const bool work = act && !lq;
+            // hit 0 defines the window
+            int s0 = 1, p0 = 0, il0 = 0;
+            if (work && to > fr) { s0 = a.sid[fr]; p0 = a.pos[fr]; if (PAIRED) il0 = a.insertL[fr]; }
+            const int t0 = abs(s0), d0 = s0 < 0;
+            const bool has_hit = work && to > fr;
+            const double S1 = seq_prob_coop<G, HASQ>(a, prof, 0, in ? i : 0, t0, p0, d0, g, has_hit);
+            double S2 = 1.0;
+            if (PAIRED) S2 = seq_prob_coop<G, HASQ>(a, prof, 1, in ? i : 0, t0, a.tot_len[t0] - p0 - il0, !d0, g, has_hit);
+            const double P1 = noise_prob_coop<G, HASQ>(a, nprof, 0, in ? i : 0, g, work);
+            double P2 = 1.0;
+            if (PAIRED) P2 = noise_prob_coop<G, HASQ>(a, nprof, 1, in ? i : 0, g, work);
+            if (act && g == 0) a.ncpv[i] = lq ? 0.0 : noise_conprb<HASQ, true>(a, nprof, i, P1, P2);
+            if (act)
+                for (unsigned long long j = fr + g; j < to; j += G) {
+                    double v = 0.0;
+                    if (!lq)
+                        v = PAIRED ? conprb_paired<HASQ, true>(a, prof, i, a.sid[j], a.pos[j], a.insertL[j], S1, S2)
+                                   : conprb_single<HASQ, true>(a, prof, i, a.sid[j], a.pos[j], S1);
+                    a.conprb[j] = v;
+                }
+        }
+        return;
+    }
     for (unsigned long long i = (unsigned long long)blockIdx.x * (kBlock / G) + threadIdx.x / G; i < a.N; i += groups_total) {
+        if (a.mode == 2 && a.uni[i]) continue;
         const unsigned long long fr = a.row_ptr[i], to = a.row_ptr[i + 1];
         const bool lq = a.lowq[i] != 0;
         if (g == 0) a.ncpv[i] = lq ? 0.0 : noise_conprb<HASQ>(a, nprof, i);
@@ -323,6 +430,59 @@ __global__ void __launch_bounds__(kBlock) conprb_kernel(const ModelArgs a) {
                            : conprb_single<HASQ>(a, prof, i, a.sid[j], a.pos[j]);
             a.conprb[j] = v;
         }
+    }
+}
+
+// ---- which reads are "uniform" (once per upload: depends on the hits, the reads' lengths and the transcripts only) --------
+// 8 bases of a transcript in read direction, one per byte, from a RefStream word
+__device__ __forceinline__ unsigned long long read_dir_bases(unsigned long long w, bool rev) {
+    if (!rev) return w;
+    const unsigned long long is4 = (w >> 2) & 0x0101010101010101ull;         // code 4 (N) stays 4
+    const unsigned long long x = 0x0303030303030303ull & ~(is4 | (is4 << 1));
+    w ^= x;                                                                   // complement: c -> 3 - c for c < 4
+    const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
+    return ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | (unsigned long long)__byte_perm(hi, 0, 0x0123);
+}
+
+template <int G, bool PAIRED>
+__global__ void __launch_bounds__(kBlock) window_uniform_kernel(const ModelArgs a, unsigned char* uni) {
+    const int lane = threadIdx.x & 31, g = lane % G, grp = lane / G;
+    const unsigned group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    const unsigned long long groups_total = (unsigned long long)gridDim.x * (kBlock / G);
+    const unsigned long long base0 = (unsigned long long)blockIdx.x * (kBlock / G) + threadIdx.x / G;
+    const unsigned long long n_iter = (a.N + groups_total - 1) / groups_total;
+    for (unsigned long long it = 0; it < n_iter; ++it) {
+        const unsigned long long i = base0 + it * groups_total;
+        const bool in = i < a.N;
+        unsigned long long fr = 0, to = 0;
+        if (in) { fr = a.row_ptr[i]; to = a.row_ptr[i + 1]; }
+        bool same = in && to > fr;
+        int s0 = 1, p0 = 0, il0 = 0;
+        if (same) { s0 = a.sid[fr]; p0 = a.pos[fr]; if (PAIRED) il0 = a.insertL[fr]; }
+        for (unsigned long long j = fr + g; j < to; j += G) {   // lanes diverge only in the trip count
+            const int sj = a.sid[j], pj = a.pos[j], ilj = PAIRED ? a.insertL[j] : 0;
+            for (int mt = 0; mt < (PAIRED ? 2 : 1) && same; ++mt) {
+                const int len = (int)(a.roff[mt][i + 1] - a.roff[mt][i]);
+                int t[2], p[2], d[2];
+                t[0] = abs(s0); t[1] = abs(sj);
+                d[0] = (s0 < 0) ^ (mt == 1); d[1] = (sj < 0) ^ (mt == 1);
+                p[0] = mt == 0 ? p0 : a.tot_len[t[0]] - p0 - il0;
+                p[1] = mt == 0 ? pj : a.tot_len[t[1]] - pj - ilj;
+                if (p[0] < 0 || p[0] + len > a.tot_len[t[0]] || p[1] < 0 || p[1] + len > a.tot_len[t[1]]) { same = false; break; }
+                if (len <= 0) continue;
+                RefStream r0(a.seq + a.seq_off[t[0]] + (d[0] == 0 ? p[0] : a.tot_len[t[0]] - 1 - p[0]), d[0] != 0, a.seq, true);
+                RefStream r1(a.seq + a.seq_off[t[1]] + (d[1] == 0 ? p[1] : a.tot_len[t[1]] - 1 - p[1]), d[1] != 0, a.seq, true);
+                for (int k0 = 0; k0 < len && same; k0 += 8) {
+                    const bool more = k0 + 8 < len;
+                    unsigned long long w0 = read_dir_bases(r0.next(more), d[0] != 0), w1 = read_dir_bases(r1.next(more), d[1] != 0);
+                    const int n = min(8, len - k0);
+                    if (n < 8) { const unsigned long long msk = (1ull << (8 * n)) - 1ull; w0 &= msk; w1 &= msk; }
+                    if (w0 != w1) same = false;
+                }
+            }
+        }
+        const unsigned bad = __ballot_sync(0xffffffffu, in && !same) & group_mask;
+        if (in && g == 0) uni[i] = bad == 0u ? 1 : 0;
     }
 }
 
@@ -418,6 +578,7 @@ __global__ void __launch_bounds__(kBlock) update_kernel(const ModelArgs a) {
     const unsigned long long groups_total = (unsigned long long)gridDim.x * (kBlock / G);
     for (unsigned long long i = (unsigned long long)blockIdx.x * (kBlock / G) + threadIdx.x / G; i < a.N; i += groups_total) {
         if (a.lowq[i]) continue;
+        if (a.mode == 2 && a.uni[i]) continue;   // handled by update_coop_kernel
         const unsigned long long fr = a.row_ptr[i], to = a.row_ptr[i + 1];
         if (g == 0) {
             const double f0 = a.post0[i];
@@ -491,7 +652,7 @@ __global__ void __launch_bounds__(kQMaxWarps * 32, 1) update_q_kernel(const Mode
     const unsigned long long warps_total = (unsigned long long)gridDim.x * kQWarps;
     for (unsigned long long base = ((unsigned long long)blockIdx.x * kQWarps + warp) * R; base < a.N; base += warps_total * R) {
         const unsigned long long i = base + grp;
-        const bool valid = i < a.N && !a.lowq[i];
+        const bool valid = i < a.N && !a.lowq[i] && !(a.mode == 2 && a.uni[i]);   // uniform reads: update_coop_kernel
         unsigned long long fr = 0, to = 0;
         double f0 = 0.0;
         if (valid) {
@@ -635,6 +796,120 @@ __global__ void __launch_bounds__(kQMaxWarps * 32, 1) update_q_kernel(const Mode
     }
 }
 
+// ---- K3 for "uniform" reads (all hits show the read the same bases) ---------------------------------------------------
+// The profile statistics of such a read are W = sum of its hits' posteriors added once per base, whatever the number of
+// hits: the G lanes of the read's group each take a contiguous range of 8-base chunks of the window of hit 0 and add W
+// (and the noise posterior) per base - to the warp's private shared-memory tables for the quality models (QProfile:
+// ~20 hot cells), to a replica of the global block for the position-indexed Profile.  Per-hit statistics (fragment
+// length histogram, RSPD bins) are added by the lanes that own the hits.  Posteriors below 1e-300 are skipped
+// (SingleQModel.h:172, 204).
+template <int G, bool HASQ, bool PAIRED>
+__global__ void __launch_bounds__(kQMaxWarps * 32, 1) update_coop_kernel(const ModelArgs a) {
+    extern __shared__ double q_tabs[];
+    const int n_warps = blockDim.x >> 5;
+    const int n_prof = a.q_rows * 25, kQTab = a.q_rows * 30;
+    constexpr int R = 32 / G;
+    constexpr int NM = PAIRED ? 2 : 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane % G, grp = lane / G;
+    double* blk = a.stats + (size_t)((blockIdx.x * n_warps + warp) % kReplicas) * a.stats_block;
+    double* tprof = HASQ ? q_tabs + warp * kQTab : blk;
+    double* tnoise = HASQ ? tprof + n_prof : blk + a.o_noise;
+    if (HASQ) {
+        for (int k = lane; k < kQTab; k += 32) tprof[k] = 0.0;
+        __syncwarp();
+    }
+    double* t_gld = blk + a.o_gld;
+    double* t_rspd = blk + a.o_rspd;
+    const DevModel& m = a.m;
+    const unsigned long long warps_total = (unsigned long long)gridDim.x * n_warps;
+    for (unsigned long long base = ((unsigned long long)blockIdx.x * n_warps + warp) * R; base < a.N; base += warps_total * R) {
+        const unsigned long long i = base + grp;
+        const bool valid = i < a.N && !a.lowq[i] && a.uni[i];
+        if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
+        unsigned long long fr = 0, to = 0;
+        double f0 = 0.0;
+        if (valid) {
+            fr = a.row_ptr[i];
+            to = a.row_ptr[i + 1];
+            f0 = a.post0[i];
+            if (f0 < kEpsilon) f0 = 0.0;
+        }
+        int len[NM];
+        unsigned long long ro[NM];
+#pragma unroll
+        for (int mt = 0; mt < NM; ++mt) {
+            ro[mt] = valid ? a.roff[mt][i] : 0ull;
+            len[mt] = valid ? (int)(a.roff[mt][i + 1] - ro[mt]) : 0;
+        }
+        // per-hit statistics and the summed posterior
+        double wsum = 0.0;
+        for (unsigned long long j = fr + g; j < to; j += G) {
+            const double frac = a.post[j];
+            if (frac < kEpsilon) continue;
+            wsum += frac;
+            const int sgn = a.sid[j], t = abs(sgn), dir = sgn < 0, p = a.pos[j];
+            const int fullLen = a.full_len[t], totLen = a.tot_len[t];
+            if (!PAIRED) {
+                if (m.est_rspd) {  // one strand only (SingleQModel.h:180-184; helper models have mld == NULL)
+                    if (m.ori[0] >= 0.1 && dir == 0) rspd_update(a, t_rspd, p, fullLen, frac);
+                    if (m.ori[0] < 0.1 && dir == 1) rspd_update(a, t_rspd, totLen - p - len[0], fullLen, frac);
+                }
+            } else {
+                const int il = a.insertL[j];
+                if (il > a.gld_lb && il <= a.gld_lb + a.gld_span) red_add(t_gld + (il - a.gld_lb), frac);
+                if (m.est_rspd) rspd_update(a, t_rspd, dir == 0 ? p : totLen - p - il, fullLen, frac);
+            }
+        }
+        const double W = lane_group_sum<G>(wsum);
+        // the window: hit 0
+        int s0 = 1, p0 = 0, il0 = 0;
+        if (valid && to > fr) { s0 = a.sid[fr]; p0 = a.pos[fr]; if (PAIRED) il0 = a.insertL[fr]; }
+        const int t0 = abs(s0), d0 = s0 < 0, totLen0 = a.tot_len[t0];
+#pragma unroll
+        for (int mt = 0; mt < NM; ++mt) {
+            if (!valid || len[mt] <= 0 || (W == 0.0 && f0 == 0.0)) continue;
+            const int n_chunks = (len[mt] + 7) >> 3;
+            const int c0 = g * n_chunks / G, c1 = (g + 1) * n_chunks / G;
+            if (c1 <= c0) continue;
+            const int mpos = mt == 0 ? p0 : totLen0 - p0 - il0, mdir = mt == 0 ? d0 : !d0;
+            const bool prof_on = W != 0.0 && to > fr;
+            FwdBytes rb(a.rbase[mt] + ro[mt] + 8 * c0);
+            FwdBytes rq(HASQ ? a.rqual[mt] + ro[mt] + 8 * c0 : a.rbase[mt] + ro[mt], HASQ);
+            RefStream sb(a.seq + (prof_on ? a.seq_off[t0] + (mdir == 0 ? mpos + 8 * c0 : totLen0 - 1 - mpos - 8 * c0) : 0), mdir != 0,
+                         a.seq, prof_on);
+            for (int c = c0; c < c1; ++c) {
+                const bool more = c + 1 < c1;
+                const unsigned long long ws = sb.next(prof_on && more), wr = rb.next(more), wq = HASQ ? rq.next(more) : 0ull;
+                const int k0 = 8 * c, n = min(8, len[mt] - k0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k < n) {
+                        const int rv = (int)byte_of(wr, k);
+                        const int row = HASQ ? (int)byte_of(wq, k) : k0 + k;
+                        if (prof_on) {
+                            double* cell = tprof + (row * 5 + sb.base_at(ws, k)) * 5 + rv;
+                            if (HASQ) atomicAdd(cell, W); else red_add(cell, W);
+                        }
+                        if (f0 != 0.0) {
+                            double* cell = tnoise + (HASQ ? row * 5 + rv : rv);
+                            if (HASQ) atomicAdd(cell, f0); else red_add(cell, f0);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (HASQ) {
+        __syncthreads();
+        double* out = a.stats + (size_t)(blockIdx.x % kReplicas) * a.stats_block;
+        for (int cidx = threadIdx.x; cidx < kQTab; cidx += blockDim.x) {
+            double v = 0.0;
+            for (int w = 0; w < n_warps; ++w) v += q_tabs[w * kQTab + cidx];
+            if (v != 0.0) red_add(out + (cidx < n_prof ? (size_t)cidx : a.o_noise + (size_t)(cidx - n_prof)), v);
+        }
+    }
+}
+
 __global__ void max_u8_kernel(const unsigned char* v, unsigned long long n, unsigned int* out) {
     unsigned int m = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -677,6 +952,8 @@ void fill_args(rsem_b200_ctx* c, ModelArgs& a) {
     a.post = c->post;
     a.post0 = c->post0;
     a.err_flag = c->err_flag;
+    a.uni = c->reads.uni;
+    a.mode = 0;
     const bool hasq = c->model.model_type & 1;
     int rows = hasq ? 100 : std::min(c->model.pro_len, std::max(c->reads.max_len, 1));
     if ((size_t)rows * 200 + 4096 > 200 * 1024) rows = 0;
@@ -727,9 +1004,33 @@ int launch_update_q(rsem_b200_ctx* c, const ModelArgs& a) {
     return 0;
 }
 
+template <int G, bool HASQ, bool PAIRED>
+int launch_update_coop(rsem_b200_ctx* c, const ModelArgs& a) {
+    auto k = update_coop_kernel<G, HASQ, PAIRED>;
+    const size_t per_warp = HASQ ? (size_t)a.q_rows * 30 * sizeof(double) : 0;
+    const int warps = HASQ ? (int)std::max<size_t>(1, std::min<size_t>(kQMaxWarps, (size_t)(200 * 1024) / per_warp)) : kQMaxWarps;
+    const size_t smem = per_warp * warps;
+    if (smem > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<c->sm_count * (HASQ ? 1 : 2), warps * 32, smem, c->stream>>>(a);
+    RB_CUDA(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
 template <int G>
-int launch_update_g(rsem_b200_ctx* c, const ModelArgs& a, unsigned grid) {
+int launch_update_g(rsem_b200_ctx* c, ModelArgs& a, unsigned grid) {
     const bool hasq = c->model.model_type & 1, paired = c->model.model_type >= 2;
+    a.mode = 0;
+    if (c->reads.uni_valid && !getenv("RSEM_B200_NO_COOP")) {   // uniform reads first, the per-hit kernels skip them (mode 2)
+        a.mode = 1;
+        int rc;
+        if (hasq && paired) rc = launch_update_coop<G, true, true>(c, a);
+        else if (hasq) rc = launch_update_coop<G, true, false>(c, a);
+        else if (paired) rc = launch_update_coop<G, false, true>(c, a);
+        else rc = launch_update_coop<G, false, false>(c, a);
+        if (rc) return rc;
+        a.mode = 2;
+    }
     static const bool global_reds = getenv("RSEM_B200_K3") && !strcmp(getenv("RSEM_B200_K3"), "global");
     if (hasq && !global_reds) return paired ? launch_update_q<G, true>(c, a) : launch_update_q<G, false>(c, a);
     if (hasq && paired) update_kernel<G, true, true><<<grid, kBlock, 0, c->stream>>>(a);
@@ -750,8 +1051,48 @@ unsigned grid_for(rsem_b200_ctx* c, int G) {
 
 }  // namespace
 
+// per read: do all its hits show it the same bases?  Depends on hits, read lengths and transcripts only: once per upload.
+static int ensure_uniform_flags(rsem_b200_ctx* c) {
+    if (c->reads.uni_valid) return 0;
+    if (!c->reads.uni) RB_CUDA(cudaMalloc(&c->reads.uni, c->N + 16));
+    ModelArgs a;
+    fill_args(c, a);
+    const int G = c->group;
+    const unsigned grid = grid_for(c, G);
+    const bool paired = c->model.model_type >= 2;
+#define RB_UNI(GG)                                                                                         \
+    do {                                                                                                   \
+        if (paired) window_uniform_kernel<GG, true><<<grid, kBlock, 0, c->stream>>>(a, c->reads.uni);      \
+        else window_uniform_kernel<GG, false><<<grid, kBlock, 0, c->stream>>>(a, c->reads.uni);            \
+    } while (0)
+    switch (G) {
+        case 4: RB_UNI(4); break;
+        case 8: RB_UNI(8); break;
+        case 16: RB_UNI(16); break;
+        default: RB_UNI(32); break;
+    }
+#undef RB_UNI
+    RB_CUDA(cudaGetLastError());
+    c->launches++;
+    c->reads.uni_valid = true;
+    return 0;
+}
+
+template <int G>
+static int launch_conprb_modes(rsem_b200_ctx* c, ModelArgs& a, unsigned grid, size_t smem, bool coop) {
+    if (!coop) { a.mode = 0; return launch_conprb_g<G>(c, a, grid, smem); }
+    a.mode = 1;
+    if (int rc = launch_conprb_g<G>(c, a, grid, smem)) return rc;
+    a.mode = 2;
+    return launch_conprb_g<G>(c, a, grid, smem);
+}
+
 int model_launch_conprb(rsem_b200_ctx* c) {
     if (c->N == 0) return 0;
+    // reads whose hits all show them the same bases take the cooperative path (one pass over the bases per READ instead
+    // of per hit); RSEM_B200_NO_COOP=1 keeps every read on the per-hit path (the reference's multiplication order)
+    static const bool no_coop = getenv("RSEM_B200_NO_COOP") != nullptr;
+    if (!no_coop) if (int rc = ensure_uniform_flags(c)) return rc;
     ModelArgs a;
     fill_args(c, a);
     const bool hasq = c->model.model_type & 1;
@@ -759,10 +1100,10 @@ int model_launch_conprb(rsem_b200_ctx* c) {
     const int G = c->group;
     const unsigned grid = grid_for(c, G);
     switch (G) {
-        case 4: return launch_conprb_g<4>(c, a, grid, smem);
-        case 8: return launch_conprb_g<8>(c, a, grid, smem);
-        case 16: return launch_conprb_g<16>(c, a, grid, smem);
-        default: return launch_conprb_g<32>(c, a, grid, smem);
+        case 4: return launch_conprb_modes<4>(c, a, grid, smem, !no_coop);
+        case 8: return launch_conprb_modes<8>(c, a, grid, smem, !no_coop);
+        case 16: return launch_conprb_modes<16>(c, a, grid, smem, !no_coop);
+        default: return launch_conprb_modes<32>(c, a, grid, smem, !no_coop);
     }
 }
 

@@ -20,6 +20,7 @@ struct NcclApi {
     int (*GetUniqueId)(NcclUniqueId*);
     int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int);
     int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t);
     int (*CommDestroy)(NcclComm);
     const char* (*GetErrorString)(int);
 };
@@ -42,6 +43,7 @@ const NcclApi* nccl_api() {
     g_api.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(h, "ncclGetUniqueId");
     g_api.CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(h, "ncclCommInitRank");
     g_api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_api.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(h, "ncclAllGather");
     g_api.CommDestroy = (int (*)(NcclComm))dlsym(h, "ncclCommDestroy");
     g_api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
     if (!g_api.GetUniqueId || !g_api.CommInitRank || !g_api.AllReduce || !g_api.CommDestroy) {
@@ -84,6 +86,15 @@ int nccl_allreduce_sum_f64(void* comm, double* buf, size_t n, cudaStream_t strea
     if (!api) return RSEM_B200_ERR_NCCL;
     int rc = api->AllReduce(buf, buf, n, kNcclFloat64, kNcclSum, comm, stream);
     if (rc != kNcclSuccess) return nccl_fail(api, rc, "ncclAllReduce");
+    return 0;
+}
+
+int nccl_allgather_bytes(void* comm, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream) {
+    const NcclApi* api = nccl_api();
+    if (!api) return RSEM_B200_ERR_NCCL;
+    if (!api->AllGather) { set_error("libnccl.so.2 lacks ncclAllGather"); return RSEM_B200_ERR_NCCL; }
+    int rc = api->AllGather(send, recv, bytes_per_rank, /* ncclInt8 */ 0, comm, stream);
+    if (rc != kNcclSuccess) return nccl_fail(api, rc, "ncclAllGather");
     return 0;
 }
 
