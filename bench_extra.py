@@ -20,16 +20,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 
 def _ofg_matrix(N, M, deg, seed):
     """the matrix rsem-run-em --gibbs-out hands to rsem-run-gibbs (Gibbs.cpp:119-131): per read the noise entry (sid 0)
-    first, then its hits; isoform families are runs of consecutive ids"""
+    first, then its hits.  Transcripts form disjoint isoform families of 1 + Poisson(deg - 1) consecutive ids (genes);
+    a read comes from one family (expression weights u^4: long tailed, as in tools/gen_dataset) and hits a run of its
+    members - so the read x transcript graph falls into one connected component per family, as real data does per gene."""
     rng = np.random.default_rng(seed)
-    degs = np.minimum(1 + rng.poisson(deg - 1, N), M).astype(np.int64)
+    sizes = []
+    tot = 0
+    while tot < M:
+        k = min(int(1 + rng.poisson(deg - 1)), M - tot)
+        sizes.append(k)
+        tot += k
+    sizes = np.array(sizes, np.int64)
+    fam_start = np.concatenate([[1], 1 + np.cumsum(sizes)[:-1]])
+    wgt = rng.random(len(sizes)) ** 4 + 1e-6
+    fam = rng.choice(len(sizes), size=N, p=wgt / wgt.sum())
+    fsz = sizes[fam]
+    degs = np.maximum(1, np.minimum(fsz, np.where(rng.random(N) < 0.8, fsz, 1 + (rng.random(N) * fsz).astype(np.int64))))
+    first = fam_start[fam] + ((fsz - degs) * rng.random(N)).astype(np.int64)
     w = degs + 1  # + noise entry
     row_ptr = np.zeros(N + 1, np.uint64)
     row_ptr[1:] = np.cumsum(w)
     E = int(row_ptr[-1])
-    start = np.minimum(rng.integers(1, M + 1, N), M - degs + 1).clip(1)
     within = np.arange(E, dtype=np.int64) - np.repeat(row_ptr[:-1].astype(np.int64), w)
-    sid = (np.repeat(start, w) + within - 1).astype(np.int32)
+    sid = (np.repeat(first, w) + within - 1).astype(np.int32)
     sid[within == 0] = 0
     val = np.empty(E)
     CH = 20_000_000

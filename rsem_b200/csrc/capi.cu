@@ -87,6 +87,9 @@ void free_gibbs(rsem_b200_ctx* c) {
     if (c->gibbs.p_sid) cudaFree(c->gibbs.p_sid);
     if (c->gibbs.p_con) cudaFree(c->gibbs.p_con);
     if (c->gibbs.seg_start) cudaFree(c->gibbs.seg_start);
+    if (c->gibbs.seg_ntr) cudaFree(c->gibbs.seg_ntr);
+    if (c->gibbs.seg_tid_off) cudaFree(c->gibbs.seg_tid_off);
+    if (c->gibbs.comp_tids) cudaFree(c->gibbs.comp_tids);
     c->gibbs = DevGibbs{};
 }
 

@@ -105,6 +105,9 @@ struct DevGibbs {
     int32_t* p_sid = nullptr;
     double* p_con = nullptr;
     int32_t* seg_start = nullptr;  // n_segs + 1 offsets into `order`
+    int32_t* seg_ntr = nullptr;    // transcripts per component; < 32: rows (p_sid) and assignments hold local ids
+    int32_t* seg_tid_off = nullptr;
+    int32_t* comp_tids = nullptr;  // sorted transcript ids of every component
     int32_t n_segs = 0;
     uint32_t max_len = 0;
 };

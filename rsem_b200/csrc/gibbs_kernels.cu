@@ -274,8 +274,9 @@ struct ChainSync {
     unsigned u_ready;           // generator -> workers: uniforms of sweeps < u_ready are complete
     unsigned sweeps_done;       // workers -> generator: sweeps < sweeps_done no longer need their uniform buffer
     unsigned changed;           // some flip word differs between the pass's input and output sets
+    unsigned next_seg;          // next component to be claimed in the current pass
     int err;
-    unsigned passes, pad;       // diagnostics: passes run over all sweeps
+    unsigned passes;            // diagnostics: passes run over all sweeps
     unsigned long long prof[4]; // clock64 totals of worker CTA 0: wait for uniforms, passes, barriers + bookkeeping, per-sample work
 };
 
@@ -286,6 +287,9 @@ struct PArgs {
     const int* p_sid;
     const double* p_con;
     const int* seg_start;               // n_segs + 1 slot offsets
+    const int* seg_ntr;                 // transcripts of the component (0: the segment is a read with only the noise entry)
+    const int* seg_tid_off;             // offset of the component's sorted transcript ids in comp_tids
+    const int* comp_tids;
     int n_segs;
     int M, burnin, gap, n_genes, n_chains, ctas_per_chain, chain_base;
     const int* chain_samples;
@@ -387,136 +391,187 @@ __device__ void generator_loop(const PArgs& a, ChainSync* sy, unsigned* ubuf, un
     }
 }
 
-// A thread walks the reads of one component (segment) in order.  The static part of a read (ids, conprb, its
-// uniform, its previous assignment) does not depend on the counts, so the next read's row is loaded into registers
-// while the current one is drawn: the only memory round trip left on the dependent chain of a read is the gather of
-// its candidates' counts.  Rows of up to kRowRegs entries take this register path; longer rows take the generic
-// two-pass loop that recomputes the same running sum, bit for bit.
-constexpr int kRowRegs = 12;
+// A group of kGL = 16 lanes walks the reads of one component (segment) in order; the lanes hold the entries of the
+// current row.  What is sequential in the reference stays sequential - reads in order, the left-to-right fp64 running
+// sum of a row - everything else is spread over the lanes:
+//   * the next row (header, ids, conprb) is loaded while the current one is drawn;
+//   * REG components (<= 31 transcripts: a gene family) keep their counts in REGISTERS - lane j owns local ids j and
+//     j + 16, a lookup is a 16-wide shuffle, an update a predicated add - so the dependent chain of a read contains no
+//     memory round trip at all; their rows and assignments are stored as local ids (0 = noise);
+//   * larger components read and write their counts in L2 (component-private, ld.cg / st.cg);
+//   * the running sum is formed by every lane for its own prefix from the row's products in shared memory, in entry
+//     order (bit-identical to arr[k] += arr[k - 1], Gibbs.cpp:286-288, 301-308); the drawn index is the number of
+//     entries <= u * total (sampling.h:50-65 on a non-decreasing array).
+constexpr int kGL = 16;
 
-struct RowRegs {
+struct GroupSmem {
+    double v[kGL];         // products of the current chunk
+    double al[2 * kGL];    // REG: alpha of the component's local ids
+};
+
+struct RowHead {
     int i;                 // read id (position in the sweep order)
     unsigned len;
     unsigned long long off;
     int zo;                // assignment left by the previous sweep
-    unsigned raw;          // MT19937 output for this read in this sweep
-    int t[kRowRegs];
-    double c[kRowRegs];
+    unsigned raw;          // MT19937 output of this read in this sweep
+    int t;                 // this lane's entry of the first chunk (id or local id)
+    double c;
 };
 
-__device__ __forceinline__ void load_row(const PArgs& a, const int* z_prev, const unsigned* u, int q, bool use_counts, RowRegs& r) {
+__device__ __forceinline__ void load_head(const PArgs& a, const int* z_prev, const unsigned* u, int q, bool use_counts, int gl, RowHead& r) {
     r.i = a.order[q];
     r.off = a.p_off[q];
     r.len = (unsigned)(a.p_off[q + 1] - r.off);
     r.zo = use_counts ? ld_cg(z_prev + q) : 0;
     r.raw = __ldcg(u + r.i);
-#pragma unroll
-    for (int k = 0; k < kRowRegs; ++k) {
-        r.t[k] = k < (int)r.len ? a.p_sid[r.off + k] : 0;
-        r.c[k] = k < (int)r.len ? a.p_con[r.off + k] : 0.0;
-    }
+    const bool in = (unsigned)gl < r.len;
+    r.t = in ? a.p_sid[r.off + gl] : -1;
+    r.c = in ? a.p_con[r.off + gl] : 0.0;
 }
 
-// Returns the new assignment and updates the counts of the component (plain stores: component-private).  counts[0] is
-// never touched here: c0 is the noise count this read sees, membership changes are recorded by the caller.
-// The row is processed in chunks of kRowRegs entries: ids / conprb of a chunk with independent loads (the first chunk
-// was prefetched with the row), then the counts and alphas of the chunk with independent gathers, then the
-// left-to-right running sum.  The running sums and the counts seen are kept in a per-thread local array so that the
-// search needs no second trip to memory.  All lanes run the same code; rows differ only in the number of chunks.
-constexpr int kMaxLocal = 8 * kRowRegs;   // rows up to 96 entries; longer ones take the generic loop below
+// prefix sums of the chunk's products in entry order; lane gl gets arr[base + gl]; returns the running sum after the chunk
+__device__ __forceinline__ double chunk_running_sum(GroupSmem& sm, unsigned gmask, int gl, double v, unsigned base, unsigned n_valid,
+                                                    double carry, double& arr) {
+    sm.v[gl] = v;
+    __syncwarp(gmask);
+    double run = carry;
+    for (unsigned j = 0; j < n_valid; ++j) {
+        const double x = sm.v[j];
+        if ((int)j <= gl) run = (base + j) ? __dadd_rn(x, run) : x;
+    }
+    arr = run;
+    const double last = __shfl_sync(gmask, run, (int)n_valid - 1, kGL);
+    __syncwarp(gmask);
+    return last;
+}
 
-__device__ __forceinline__ int draw_row(const PArgs& a, int* counts, const RowRegs& r, bool use_counts, int c0, int* err) {
-    const double u = r.raw * (1.0 / 4294967296.0);
-    const int zo = r.zo;
-    if (r.len <= kMaxLocal) {
-        double arr[kMaxLocal];
-        int seen[kMaxLocal];
-        double run = 0.0;
-        int cnt_zo = 0;
-        for (unsigned base = 0; base < r.len; base += kRowRegs) {
-            int t[kRowRegs];
-            double c[kRowRegs];
-            if (base == 0) {
-#pragma unroll
-                for (int k = 0; k < kRowRegs; ++k) { t[k] = r.t[k]; c[k] = r.c[k]; }
+template <bool REG>
+__device__ __forceinline__ void walk_segment(const PArgs& a, int seg, bool use_counts, int* counts, const int* z_prev, int* z_cur,
+                                             const unsigned* u, int c0_start, const unsigned* f_in, unsigned* f_out, const int* pre,
+                                             const int* sh_base, unsigned w_per, unsigned W, int* err, GroupSmem& sm, unsigned gmask, int gl) {
+    const int q0 = a.seg_start[seg], q_end = a.seg_start[seg + 1];
+    const int K = a.seg_ntr[seg];
+    const int* tids = a.comp_tids + a.seg_tid_off[seg];
+    int cnt0 = 0, cnt1 = 0;   // REG: counts of local ids gl and gl + 16
+    if (REG) {
+        if (gl >= 1 && gl <= K) cnt0 = ld_cg(counts + tids[gl - 1]);
+        if (gl + kGL <= K) cnt1 = ld_cg(counts + tids[gl + kGL - 1]);
+        sm.al[gl] = a.alpha[(gl >= 1 && gl <= K) ? tids[gl - 1] : 0];
+        sm.al[gl + kGL] = a.alpha[gl + kGL <= K ? tids[gl + kGL - 1] : 0];
+        __syncwarp(gmask);
+    }
+    RowHead nxt;
+    load_head(a, z_prev, u, q0, use_counts, gl, nxt);
+    for (int q = q0; q < q_end; ++q) {
+        const RowHead cur = nxt;
+        if (q + 1 < q_end) load_head(a, z_prev, u, q + 1, use_counts, gl, nxt);   // in flight while `cur` is drawn
+        int c0 = c0_start;
+        if (use_counts) {   // noise count seen by read i: flips of the input set before position i
+            const unsigned w = (unsigned)cur.i >> 5, m = (1u << ((unsigned)cur.i & 31u)) - 1u;
+            c0 += sh_base[w / w_per] + ld_cg(pre + w) + __popc(__ldcg(f_in + w) & m) - __popc(__ldcg(f_in + W + w) & m);
+        }
+        const double uni = cur.raw * (1.0 / 4294967296.0);
+        const int zo = cur.zo;
+        // value of one entry: (count + alpha) * conprb with the read's own assignment taken out (Gibbs.cpp:298-306)
+        auto entry_value = [&](int t, double c, bool valid, int& cnt_seen) -> double {
+            int cnt = c0;
+            double al;
+            if (REG) {
+                const int src = valid ? (t & (kGL - 1)) : 0;
+                const int x0 = __shfl_sync(gmask, cnt0, src, kGL), x1 = __shfl_sync(gmask, cnt1, src, kGL);
+                if (valid && t != 0) cnt = t < kGL ? x0 : x1;
+                al = sm.al[valid ? t : 0];
             } else {
-#pragma unroll
-                for (int k = 0; k < kRowRegs; ++k) {
-                    const bool in = base + k < r.len;
-                    t[k] = in ? a.p_sid[r.off + base + k] : 0;
-                    c[k] = in ? a.p_con[r.off + base + k] : 0.0;
-                }
+                if (valid && t != 0) cnt = ld_cg(counts + t);
+                al = a.alpha[valid ? t : 0];
             }
-            if (use_counts) {
-                int cnt[kRowRegs];
-                double al[kRowRegs];
-#pragma unroll
-                for (int k = 0; k < kRowRegs; ++k) {
-                    cnt[k] = (base + k < r.len && t[k] != 0) ? ld_cg(counts + t[k]) : c0;
-                    al[k] = a.alpha[t[k]];
-                }
-#pragma unroll
-                for (int k = 0; k < kRowRegs; ++k) {
-                    if (t[k] == zo) cnt[k] -= 1;   // --counts[z_i] (Gibbs.cpp:298), seen by every entry of that transcript
-                    if (base + k < r.len && t[k] == zo) cnt_zo = cnt[k];
-                    c[k] = __dmul_rn(__dadd_rn((double)cnt[k], al[k]), c[k]);
-                    seen[base + k] = cnt[k];
-                }
+            if (valid && t == zo) cnt -= 1;
+            cnt_seen = cnt;
+            if (!valid) return 0.0;
+            return use_counts ? __dmul_rn(__dadd_rn((double)cnt, al), c) : c;
+        };
+        int znew;
+        if (cur.len <= (unsigned)kGL) {
+            const bool valid = (unsigned)gl < cur.len;
+            int seen;
+            const double v = entry_value(cur.t, cur.c, valid, seen);
+            double arr;
+            const double total = chunk_running_sum(sm, gmask, gl, v, 0u, cur.len, 0.0, arr);
+            const double prb = __dmul_rn(uni, total);
+            int l = __popc(__ballot_sync(gmask, valid && arr <= prb));
+            if (l >= (int)cur.len) { *err = 3; l = (int)cur.len - 1; }   // reference: assert(l < len), sampling.h:62
+            znew = __shfl_sync(gmask, cur.t, l, kGL);
+            if (!REG && use_counts && znew != zo) {   // the lanes that hold the two entries know the counts they saw
+                if (valid && zo != 0 && cur.t == zo) st_cg(counts + zo, seen);
+                if (gl == l && znew != 0) st_cg(counts + znew, seen + 1);
             }
-#pragma unroll
-            for (int k = 0; k < kRowRegs; ++k) {   // left-to-right running sum; slots beyond len repeat the last value
-                if (base + k < r.len) run = (base + k) ? __dadd_rn(c[k], run) : c[k];
-                arr[base + k] = run;
+            if (!REG && !use_counts && gl == l && znew != 0) st_cg(counts + znew, ld_cg(counts + znew) + 1);
+        } else {
+            // rows longer than a group: one pass for the total, one for the index
+            double carry = 0.0;
+            for (unsigned base = 0; base < cur.len; base += kGL) {
+                const unsigned k = base + gl, nv = min((unsigned)kGL, cur.len - base);
+                const bool valid = k < cur.len;
+                const int t = valid ? a.p_sid[cur.off + k] : -1;
+                const double c = valid ? a.p_con[cur.off + k] : 0.0;
+                int seen;
+                double arr;
+                carry = chunk_running_sum(sm, gmask, gl, entry_value(t, c, valid, seen), base, nv, carry, arr);
+            }
+            const double prb = __dmul_rn(uni, carry);
+            int l = 0;
+            carry = 0.0;
+            znew = -1;
+            for (unsigned base = 0; base < cur.len; base += kGL) {
+                const unsigned k = base + gl, nv = min((unsigned)kGL, cur.len - base);
+                const bool valid = k < cur.len;
+                const int t = valid ? a.p_sid[cur.off + k] : -1;
+                const double c = valid ? a.p_con[cur.off + k] : 0.0;
+                int seen;
+                double arr;
+                carry = chunk_running_sum(sm, gmask, gl, entry_value(t, c, valid, seen), base, nv, carry, arr);
+                const int below = __popc(__ballot_sync(gmask, valid && arr <= prb));
+                l += below;
+                if (znew < 0 && below < (int)nv) znew = __shfl_sync(gmask, t, below, kGL);   // first entry with arr > prb (group-uniform branch)
+            }
+            if (znew < 0) {   // reference: assert(l < len)
+                *err = 3;
+                znew = a.p_sid[cur.off + cur.len - 1];
+            }
+            if (!REG && gl == 0) {
+                if (use_counts) {
+                    if (znew != zo) {
+                        if (zo != 0) st_cg(counts + zo, ld_cg(counts + zo) - 1);
+                        if (znew != 0) st_cg(counts + znew, ld_cg(counts + znew) + 1);
+                    }
+                } else if (znew != 0) st_cg(counts + znew, ld_cg(counts + znew) + 1);
             }
         }
-        const double prb = __dmul_rn(u, run);
-        int l = -1;
-        for (unsigned k = 0; k < r.len; ++k)
-            if (arr[k] > prb) { l = (int)k; break; }   // smallest index with arr[k] > prb (sampling.h:55-60)
-        if (l < 0) { *err = 3; l = (int)r.len - 1; }   // reference: assert(l < len)
-        const int zn = l < kRowRegs ? 0 : a.p_sid[r.off + l];
-        int zn_fast = 0;
-#pragma unroll
-        for (int k = 0; k < kRowRegs; ++k) if (k == l) zn_fast = r.t[k];
-        const int znew = l < kRowRegs ? zn_fast : zn;
-        if (use_counts) {
-            if (znew != zo) {
-                if (zo != 0) st_cg(counts + zo, cnt_zo);
-                if (znew != 0) st_cg(counts + znew, seen[l] + 1);
-            }
-        } else if (znew != 0) st_cg(counts + znew, ld_cg(counts + znew) + 1);
-        return znew;
+        if (REG && znew != zo) {   // owners of the two local ids adjust their registers
+            if (use_counts && zo != 0 && (zo & (kGL - 1)) == gl) { if (zo < kGL) --cnt0; else --cnt1; }
+            if (znew != 0 && (znew & (kGL - 1)) == gl) { if (znew < kGL) ++cnt0; else ++cnt1; }
+        }
+        if (gl == 0) {
+            st_cg(z_cur + q, znew);
+            if (use_counts) {
+                if (zo != 0 && znew == 0) atomicOr(f_out + ((unsigned)cur.i >> 5), 1u << ((unsigned)cur.i & 31u));
+                if (zo == 0 && znew != 0) atomicOr(f_out + W + ((unsigned)cur.i >> 5), 1u << ((unsigned)cur.i & 31u));
+            } else if (znew == 0) atomicAdd(counts, 1);
+        }
+        if (!REG) __syncwarp(gmask);   // the count stores of this read precede the next read's loads (other lanes)
     }
-    // ---- very long rows: generic two-pass loop
-    if (use_counts && zo != 0) st_cg(counts + zo, ld_cg(counts + zo) - 1);
-    const int c0_eff = c0 - (use_counts && zo == 0 ? 1 : 0);
-    double total = 0.0;
-    for (unsigned k = 0; k < r.len; ++k) {
-        const int t = a.p_sid[r.off + k];
-        const double c = a.p_con[r.off + k];
-        const double v = use_counts ? __dmul_rn(__dadd_rn((double)(t == 0 ? c0_eff : ld_cg(counts + t)), a.alpha[t]), c) : c;
-        total = k ? __dadd_rn(v, total) : v;
+    if (REG) {
+        if (gl >= 1 && gl <= K) st_cg(counts + tids[gl - 1], cnt0);
+        if (gl + kGL <= K) st_cg(counts + tids[gl + kGL - 1], cnt1);
     }
-    const double prb = __dmul_rn(u, total);
-    double run = 0.0;
-    int l = -1;
-    for (unsigned k = 0; k < r.len; ++k) {
-        const int t = a.p_sid[r.off + k];
-        const double c = a.p_con[r.off + k];
-        const double v = use_counts ? __dmul_rn(__dadd_rn((double)(t == 0 ? c0_eff : ld_cg(counts + t)), a.alpha[t]), c) : c;
-        run = k ? __dadd_rn(v, run) : v;
-        if (run > prb) { l = (int)k; break; }
-    }
-    if (l < 0) { *err = 3; l = (int)r.len - 1; }
-    const int zn = a.p_sid[r.off + l];
-    if (zn != 0) st_cg(counts + zn, ld_cg(counts + zn) + 1);
-    return zn;
 }
 
-__global__ void __launch_bounds__(kPThreads) gibbs_parallel_kernel(const PArgs a) {
+__global__ void __launch_bounds__(kPThreads, 4) gibbs_parallel_kernel(const PArgs a) {
     __shared__ double sh_red[kPThreads / 32];
     __shared__ int sh_scan[kPThreads];
     __shared__ int sh_base[512];     // exclusive prefix of the slice totals (<= 512 worker CTAs per chain)
+    __shared__ GroupSmem sh_grp[kPThreads / kGL];
     const unsigned group = a.ctas_per_chain + 1;   // worker CTAs + the generator CTA
     const int chain = a.chain_base + blockIdx.x / group;
     const unsigned cta = blockIdx.x % group;
@@ -594,34 +649,32 @@ __global__ void __launch_bounds__(kPThreads) gibbs_parallel_kernel(const PArgs a
                 __syncthreads();
             }
             const long long tp0 = clock64();
-            for (int sgm = (int)ctid; sgm < a.n_segs; sgm += (int)chain_threads) {
-                const int q_end = a.seg_start[sgm + 1];
-                int q = a.seg_start[sgm];
-                RowRegs nxt;
-                load_row(a, z_prev, u, q, use_counts, nxt);
-                for (; q < q_end; ++q) {
-                    const RowRegs cur = nxt;
-                    if (q + 1 < q_end) load_row(a, z_prev, u, q + 1, use_counts, nxt);   // in flight while `cur` is drawn
-                    int c0 = c0_start;
-                    if (use_counts) {   // noise count seen by read i: flips of the input set before position i
-                        const unsigned w = (unsigned)cur.i >> 5, m = (1u << ((unsigned)cur.i & 31u)) - 1u;
-                        c0 += sh_base[w / w_per] + ld_cg(pre + w) + __popc(__ldcg(f_in + w) & m) - __popc(__ldcg(f_in + W + w) & m);
-                    }
-                    const int zn = draw_row(a, counts, cur, use_counts, c0, &sy->err);
-                    st_cg(z_cur + q, zn);
-                    if (use_counts) {
-                        if (cur.zo != 0 && zn == 0) atomicOr(f_out + ((unsigned)cur.i >> 5), 1u << ((unsigned)cur.i & 31u));
-                        if (cur.zo == 0 && zn != 0) atomicOr(f_out + W + ((unsigned)cur.i >> 5), 1u << ((unsigned)cur.i & 31u));
-                    } else if (zn == 0) atomicAdd(counts, 1);
+            {   // groups of kGL lanes claim components, longest first (a walk is sequential: the long ones must start early)
+                const int gl = tid & (kGL - 1);
+                const unsigned gmask = 0xffffu << ((tid & 31) & ~(kGL - 1));
+                GroupSmem& gsm = sh_grp[tid / kGL];
+                for (;;) {
+                    int sgm = 0;
+                    if (gl == 0) sgm = (int)atomicAdd(&sy->next_seg, 1u);
+                    sgm = __shfl_sync(gmask, sgm, 0, kGL);
+                    if (sgm >= a.n_segs) break;
+                    if (a.seg_ntr[sgm] < 2 * kGL)
+                        walk_segment<true>(a, sgm, use_counts, counts, z_prev, z_cur, u, c0_start, f_in, f_out, pre, sh_base, w_per, W, &sy->err,
+                                           gsm, gmask, gl);
+                    else
+                        walk_segment<false>(a, sgm, use_counts, counts, z_prev, z_cur, u, c0_start, f_in, f_out, pre, sh_base, w_per, W,
+                                            &sy->err, gsm, gmask, gl);
                 }
             }
             const long long tp1 = clock64();
             if (cta == 0 && tid == 0) sy->prof[1] += tp1 - tp0;
             if (!use_counts) {
                 chain_barrier(sy, n_ctas);
+                if (cta == 0 && tid == 0) sy->next_seg = 0;   // the next pass starts behind another barrier
                 break;
             }
             chain_barrier(sy, n_ctas);
+            if (cta == 0 && tid == 0) sy->next_seg = 0;
             // compare the two sets on this CTA's slice and form the prefix sums of the output set
             bool diff = false;
             int part = 0;
@@ -888,6 +941,27 @@ int gibbs_prepare(rsem_b200_ctx* c, const uint64_t* row_ptr, const int32_t* sid)
     }
     seg_start.push_back((int32_t)N1);
     g.n_segs = (int32_t)seg_start.size() - 1;
+    // transcripts of every component (sorted) and the local id of a transcript inside its component (1.., 0 = noise):
+    // components of fewer than 32 transcripts are walked with their counts in registers, rows and assignments in local ids
+    std::vector<int32_t> lid((size_t)M + 1, 0), ntr((size_t)M + 1, 0);
+    for (int t = 1; t <= M; ++t) lid[t] = ++ntr[find(t)];
+    std::vector<int32_t> seg_ntr(g.n_segs, 0), seg_tid_off(g.n_segs + 1, 0), comp_tids;
+    {
+        std::vector<int32_t> tid_at((size_t)M + 1, 0);   // offset of root r's list
+        int32_t at_t = 0;
+        for (size_t sgi = 0; sgi < roots.size(); ++sgi) {
+            seg_ntr[sgi] = ntr[roots[sgi]];
+            seg_tid_off[sgi] = at_t;
+            tid_at[roots[sgi]] = at_t;
+            at_t += ntr[roots[sgi]];
+        }
+        for (int sgi = (int)roots.size(); sgi <= g.n_segs; ++sgi) seg_tid_off[sgi] = at_t;
+        comp_tids.assign((size_t)at_t + 1, 0);
+        for (int t = 1; t <= M; ++t) {
+            const int32_t r = find(t);
+            if (comp_reads[r]) comp_tids[(size_t)tid_at[r] + lid[t] - 1] = t;
+        }
+    }
     // rows re-laid in slot order so that a segment is one contiguous stream
     {
         const uint64_t E = row_ptr[N1];
@@ -897,7 +971,10 @@ int gibbs_prepare(rsem_b200_ctx* c, const uint64_t* row_ptr, const int32_t* sid)
         for (uint64_t q = 0; q < N1; ++q) p_off[q + 1] = p_off[q] + (row_ptr[order[q] + 1] - row_ptr[order[q]]);
         for (uint64_t q = 0; q < N1; ++q) {
             const uint64_t src = row_ptr[order[q]], n = row_ptr[order[q] + 1] - src;
-            memcpy(p_sid.data() + p_off[q], sid + src, n * sizeof(int32_t));
+            const int32_t k = comp[order[q]];
+            if (k == 0 || ntr[k] < 32) {   // register-resident component: local ids
+                for (uint64_t j = 0; j < n; ++j) p_sid[p_off[q] + j] = lid[sid[src + j]];
+            } else memcpy(p_sid.data() + p_off[q], sid + src, n * sizeof(int32_t));
         }
         RB_CUDA(cudaMalloc(&g.p_off, (N1 + 1) * sizeof(uint64_t)));
         RB_CUDA(cudaMalloc(&g.p_sid, (E + 16) * sizeof(int32_t)));
@@ -915,6 +992,12 @@ int gibbs_prepare(rsem_b200_ctx* c, const uint64_t* row_ptr, const int32_t* sid)
     }
     RB_CUDA(cudaMalloc(&g.seg_start, seg_start.size() * sizeof(int32_t)));
     RB_CUDA(cudaMemcpyAsync(g.seg_start, seg_start.data(), seg_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    RB_CUDA(cudaMalloc(&g.seg_ntr, std::max<size_t>(seg_ntr.size(), 1) * sizeof(int32_t)));
+    RB_CUDA(cudaMalloc(&g.seg_tid_off, seg_tid_off.size() * sizeof(int32_t)));
+    RB_CUDA(cudaMalloc(&g.comp_tids, comp_tids.size() * sizeof(int32_t)));
+    RB_CUDA(cudaMemcpyAsync(g.seg_ntr, seg_ntr.data(), seg_ntr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    RB_CUDA(cudaMemcpyAsync(g.seg_tid_off, seg_tid_off.data(), seg_tid_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    RB_CUDA(cudaMemcpyAsync(g.comp_tids, comp_tids.data(), comp_tids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     RB_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -931,6 +1014,7 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
     PArgs a{};
     a.N1 = g.N1;
     a.order = g.order; a.seg_start = g.seg_start; a.n_segs = g.n_segs;
+    a.seg_ntr = g.seg_ntr; a.seg_tid_off = g.seg_tid_off; a.comp_tids = g.comp_tids;
     a.p_off = reinterpret_cast<const unsigned long long*>(g.p_off); a.p_sid = g.p_sid; a.p_con = g.p_con;
     a.M = p->M; a.burnin = p->burnin; a.gap = p->gap; a.n_genes = p->n_genes; a.n_chains = nc;
     a.n0 = p->n0; a.totc = p->totc;
@@ -941,7 +1025,7 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
     int per_sm = 0;
     RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_parallel_kernel, kPThreads, 0));
     const int resident = std::max(1, per_sm) * c->sm_count;
-    int ctas = std::max(1, std::min(512, (g.n_segs + kPThreads - 1) / kPThreads));
+    int ctas = std::max(1, std::min(512, (g.n_segs * kGL + kPThreads - 1) / kPThreads));
     if (const char* e = getenv("RSEM_B200_GIBBS_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 512) ctas = v; }
     ctas = std::min(ctas, std::max(1, resident / std::min(nc, std::max(1, resident / 2)) - 1));
     const int chains_per_wave = std::max(1, std::min(nc, resident / (ctas + 1)));
