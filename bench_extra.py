@@ -44,12 +44,18 @@ def _ofg_matrix(N, M, deg, seed):
     within = np.arange(E, dtype=np.int64) - np.repeat(row_ptr[:-1].astype(np.int64), w)
     sid = (np.repeat(first, w) + within - 1).astype(np.int32)
     sid[within == 0] = 0
+    # conditional probabilities as the read models produce them: an alignment is a product of ~100 per-base match
+    # probabilities times position / fragment-length priors (1e-12 .. 1e-3), the noise entry a product of ~100 background
+    # base frequencies (~4^-100): a read leaves or joins the noise transcript only when its alignments are junk (2 % here)
     val = np.empty(E)
     CH = 20_000_000
     for a in range(0, E, CH):
         b = min(E, a + CH)
-        val[a:b] = 10.0 ** rng.uniform(-30, -3, b - a)
-    val[within == 0] *= 1e-6
+        val[a:b] = 10.0 ** rng.uniform(-12, -3, b - a)
+    noise = 10.0 ** rng.uniform(-70, -50, N)
+    junk = rng.random(N) < 0.02
+    noise[junk] = 10.0 ** rng.uniform(-14, -6, int(junk.sum()))
+    val[row_ptr[:-1].astype(np.int64)] = noise
     return row_ptr, sid, val, E
 
 
