@@ -1,7 +1,7 @@
 """In-tree build of every native artefact (called by __graft_entry__.build()).
 
   rsem_b200/librsem_b200.so   CUDA kernels + C ABI, sm_100a only
-  bin/rsem-run-em, bin/rsem-run-gibbs   C++ drop-in executables (link the .so)
+  bin/rsem-run-em, bin/rsem-run-gibbs, bin/rsem-parse-alignments   C++ drop-in executables (link the .so)
   tools/gen_dataset           synthetic intermediate-file generator (tooling)
   oracle/librsem_oracle.so    CPU restatement (test infrastructure)
   oracle/_ref/*               reference binaries, only when /root/reference is present
@@ -51,7 +51,7 @@ def build_host(force: bool = False):
     deps = common + glob.glob(os.path.join(HOST, "*.hpp")) + [os.path.join(ROOT, "include", "rsem_b200.h")]
     for m in mains:
         name = {"main_em.cpp": "rsem-run-em", "main_gibbs.cpp": "rsem-run-gibbs",
-                "main_selftest.cpp": "rsem-b200-host-selftest"}[os.path.basename(m)]
+                "main_selftest.cpp": "rsem-b200-host-selftest", "main_parse.cpp": "rsem-parse-alignments"}[os.path.basename(m)]
         out = os.path.join(ROOT, "bin", name)
         if force or _newer(out, deps + [os.path.join(ROOT, "rsem_b200", "librsem_b200.so")]):
             _run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", out, m, *shared,

@@ -328,6 +328,54 @@ void AlnReader::parse_sam_line(const std::string& ln, BamRecord& rec) const {
 // ---- BamRecord helpers ------------------------------------------------------------------------------------------------
 uint16_t BamRecord::flag() const { return (uint16_t)(rd_u32(data.data() + 12) >> 16); }
 int32_t BamRecord::tid() const { return (int32_t)rd_u32(data.data()); }
+int32_t BamRecord::pos() const { return (int32_t)rd_u32(data.data() + 4); }
+int32_t BamRecord::l_seq() const { return (int32_t)rd_u32(data.data() + 16); }
+const char* BamRecord::qname() const { return reinterpret_cast<const char*>(data.data() + 32); }
+uint32_t BamRecord::n_cigar() const { return rd_u32(data.data() + 12) & 0xffff; }
+uint32_t BamRecord::cigar(uint32_t i) const { return rd_u32(data.data() + 32 + data[8] + 4 * (size_t)i); }
+int BamRecord::base4(int32_t i) const {
+    const uint8_t b = data[32 + data[8] + 4 * (size_t)n_cigar() + (size_t)(i >> 1)];
+    return (i & 1) ? (b & 15) : (b >> 4);
+}
+const uint8_t* BamRecord::qual() const { return data.data() + 32 + data[8] + 4 * (size_t)n_cigar() + ((size_t)l_seq() + 1) / 2; }
+
+// bam_aux_get + bam_aux2i of htslib 1.3 (SamParser.h:63-68 reads the aligner's "too many alignments" tag with them):
+// the first field with this tag; its value if the type is one of cCsSiI, 0 for any other type
+bool BamRecord::aux_int(const char tag[2], long long& value) const {
+    size_t at = 32 + data[8] + 4 * (size_t)n_cigar() + ((size_t)l_seq() + 1) / 2 + (size_t)l_seq();
+    while (at + 3 <= data.size()) {
+        const char t0 = (char)data[at], t1 = (char)data[at + 1], type = (char)data[at + 2];
+        const size_t val_at = at + 3;
+        size_t len;
+        if (type == 'Z' || type == 'H') {
+            len = 0;
+            while (val_at + len < data.size() && data[val_at + len]) ++len;
+            ++len;
+        } else if (type == 'B') {
+            if (val_at + 5 > data.size()) die("Corrupt optional field in a BAM record!");
+            len = 5 + (size_t)aux_type_size((char)data[val_at]) * rd_u32(data.data() + val_at + 1);
+        } else {
+            len = (size_t)aux_type_size(type);
+            if (len == 0) die("Corrupt optional field in a BAM record!");
+        }
+        if (val_at + len > data.size()) die("Corrupt optional field in a BAM record!");
+        if (t0 == tag[0] && t1 == tag[1]) {
+            const uint8_t* v = data.data() + val_at;
+            switch (type) {
+                case 'c': value = (int8_t)v[0]; break;
+                case 'C': value = v[0]; break;
+                case 's': value = (int16_t)rd_u16(v); break;
+                case 'S': value = rd_u16(v); break;
+                case 'i': value = (int32_t)rd_u32(v); break;
+                case 'I': value = rd_u32(v); break;
+                default: value = 0;
+            }
+            return true;
+        }
+        at = val_at + len;
+    }
+    return false;
+}
 
 // MAPQ + ZW:f from the posterior (BamWriter.h:39-48, sam_utils.h:72-76)
 void BamRecord::set_alignment_weight(double prb) {

@@ -76,6 +76,26 @@ struct HitStore {
 };
 void load_dat(const std::string& path, int read_type, uint64_t expect_n1, HitStore& out);
 
+// ---- binary side-car imd.b200 (sidecar.cpp): the hand-off from bin/rsem-parse-alignments to bin/rsem-run-em -----------
+// The text files (.dat, read files) stay the contract and are always written; the side-car holds the same content in the
+// layout rsem-run-em uploads (CSR + SoA hit fields, base / quality codes with offsets), so the text parse
+// (HitContainer.h:62-79, the ReadReader loops of EM.cpp:195-202) is skipped when it is present and still describes
+// the text files (sizes recorded in its header).  RSEM_B200_SIDECAR=0 disables writing and reading it.
+struct ShortRead { uint64_t index; std::string name; };
+struct Sidecar {
+    int read_type = 0;
+    HitStore hits;
+    ReadStore reads[3];                    // tag 0 "un", 1 "alignable", 2 "max"; lowq is NOT stored (needs seedLen / polyA)
+    std::vector<ShortRead> shorts[3];      // names of the reads with a mate shorter than kSidecarShortLen (for the warnings)
+};
+constexpr int kSidecarShortLen = 64;
+bool sidecar_enabled();
+void write_sidecar(const std::string& imd_name, const Sidecar& sc);
+bool load_sidecar(const std::string& imd_name, int read_type, Sidecar& out);   // false: absent, stale or disabled
+// lowq flags and the short-read names from codes, as parse_reads derives them from text
+void finish_sidecar_reads(ReadStore& rs, const std::vector<ShortRead>& shorts, bool has_polyA, int seed_len,
+                          std::vector<std::string>* short_names, uint64_t* n_short);
+
 // imd.ofg (EM.cpp:435-457 writer, Gibbs.cpp:101-137 reader); both split the rows over g_io_threads
 void write_ofg(const std::string& path, int M, uint64_t N0, const HitStore& h, const std::vector<double>& conprb,
                const std::vector<double>& ncpv);
@@ -134,7 +154,8 @@ struct HostModel {
     size_t n_noise() const { return hasq() ? 500 : 5; }
 
     void init_master(int model_type, const ModelParamsH& p, const RefData* refs);  // Model(ModelParams&, true)
-    void estimate_from_reads(const std::string& imd_name, ReadStore& alignable);    // estimateFromReads
+    // estimateFromReads; `sc` (optional) supplies the read sets already decoded (binary side-car)
+    void estimate_from_reads(const std::string& imd_name, ReadStore& alignable, Sidecar* sc = nullptr);
     // init(); collect(helpers); finish()  (EM.cpp:400-404) from the device sufficient statistics
     void rebuild(const rsem_b200_model_stats& st);
     void calc_mw();
@@ -166,6 +187,17 @@ struct BamRecord {
     int32_t tid() const;
     bool mapped() const { return !(flag() & 0x4); }
     bool read1() const { return flag() & 0x40; }
+    bool read2() const { return flag() & 0x80; }
+    bool paired() const { return flag() & 0x1; }
+    bool reverse() const { return flag() & 0x10; }
+    int32_t pos() const;          // 0-based leftmost position
+    int32_t l_seq() const;
+    const char* qname() const;    // NUL-terminated
+    uint32_t n_cigar() const;
+    uint32_t cigar(uint32_t i) const;   // len << 4 | op
+    int base4(int32_t i) const;   // 4-bit base code (1 A, 2 C, 4 G, 8 T, 15 N)
+    const uint8_t* qual() const;  // l_seq phred values (0xff = absent)
+    bool aux_int(const char tag[2], long long& value) const;  // bam_aux_get + bam_aux2i (0 for non-integer types)
     void set_alignment_weight(double prb);  // MAPQ + ZW:f (BamWriter.h:39-48)
 };
 
@@ -177,6 +209,7 @@ public:
     AlnReader& operator=(const AlnReader&) = delete;
     const std::string& header_text() const { return text_; }
     const std::vector<std::string>& ref_names() const { return ref_names_; }
+    const std::vector<uint32_t>& ref_lens() const { return ref_lens_; }
     bool next(BamRecord& rec);  // false at the end of the file
 
 private:

@@ -256,8 +256,17 @@ int main(int argc, char* argv[]) {
 
     // ---- init (EM.cpp:97-174): hits from .dat; the GPU holds the whole read range ----
     HitStore hits;
-    load_dat(a.imdName + ".dat", a.read_type, N1, hits);
-    stamp(".dat parsed");
+    Sidecar sidecar;   // imd.b200, written by bin/rsem-parse-alignments: the same content as .dat + the read files, decoded
+    bool have_sidecar = load_sidecar(a.imdName, a.read_type, sidecar);
+    if (have_sidecar && (sidecar.hits.N != N1 || sidecar.reads[0].n != N0 || sidecar.reads[2].n != N2 || mp.seedLen > kSidecarShortLen))
+        have_sidecar = false;   // does not describe this run: parse the text files
+    if (have_sidecar) {
+        hits = std::move(sidecar.hits);
+        stamp("binary side-car loaded (.dat and read files not parsed)");
+    } else {
+        load_dat(a.imdName + ".dat", a.read_type, N1, hits);
+        stamp(".dat parsed");
+    }
     if (g_verbose) {
         printf("Thread 0 : N = %llu, NHit = %llu\n", (unsigned long long)hits.N, (unsigned long long)hits.H);
         printf("EM_init finished!\n");
@@ -271,7 +280,7 @@ int main(int argc, char* argv[]) {
     HostModel model;
     model.init_master(a.read_type, mp, &refs);
     ReadStore reads;
-    model.estimate_from_reads(a.imdName, reads);
+    model.estimate_from_reads(a.imdName, reads, have_sidecar ? &sidecar : nullptr);
     if (reads.n != N1) die("Read indices files do not match!");
     stamp("reads parsed, initial model estimated");
 

@@ -47,8 +47,47 @@ static int bam_copy(int argc, char** argv) {
     return 0;
 }
 
+// rsem-b200-host-selftest --sidecar imdName read_type threads seedLen has_polyA outPrefix
+// loads imdName.b200 (written by bin/rsem-parse-alignments) the way rsem-run-em does and dumps the same arrays as the text
+// mode below (hits + the alignable read set with its lowq flags), plus the number / first names of the short reads.
+static int sidecar_dump(int argc, char** argv) {
+    if (argc != 8) { fprintf(stderr, "Usage: rsem-b200-host-selftest --sidecar imdName read_type threads seedLen has_polyA outPrefix\n"); return -1; }
+    const std::string imd = argv[2], out = argv[7];
+    const int read_type = atoi(argv[3]);
+    g_io_threads = atoi(argv[4]);
+    const int seed_len = atoi(argv[5]);
+    const bool has_polyA = atoi(argv[6]) != 0;
+    g_verbose = false;
+    Sidecar sc;
+    if (!load_sidecar(imd, read_type, sc)) { printf("no usable side-car\n"); return 3; }
+    dump(out + ".row_ptr.u64", sc.hits.row_ptr);
+    dump(out + ".sid.i32", sc.hits.sid);
+    dump(out + ".pos.i32", sc.hits.pos);
+    dump(out + ".insertL.i32", sc.hits.insertL);
+    unsigned long long n_short_tot = 0;
+    for (int tag = 0; tag < 3; ++tag) {
+        ReadStore& rs = sc.reads[tag];
+        std::vector<std::string> names;
+        uint64_t n_short = 0;
+        finish_sidecar_reads(rs, sc.shorts[tag], has_polyA, seed_len, &names, &n_short);
+        n_short_tot += n_short;
+        const std::string pre = out + (tag == 1 ? "" : (tag == 0 ? ".un" : ".max"));
+        for (int m = 0; m < rs.n_mates; ++m) {
+            dump(pre + ".off" + std::to_string(m) + ".u64", rs.off[m]);
+            dump(pre + ".base" + std::to_string(m) + ".u8", rs.base[m]);
+            dump(pre + ".qual" + std::to_string(m) + ".u8", rs.qual[m]);
+        }
+        dump(pre + ".lowq.u8", rs.lowq);
+        for (const std::string& nm : names) printf("short %d %s\n", tag, nm.c_str());
+    }
+    printf("N %llu H %llu reads %llu %llu %llu short %llu\n", (unsigned long long)sc.hits.N, (unsigned long long)sc.hits.H,
+           (unsigned long long)sc.reads[0].n, (unsigned long long)sc.reads[1].n, (unsigned long long)sc.reads[2].n, n_short_tot);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "--bam-copy") return bam_copy(argc, argv);
+    if (argc >= 2 && std::string(argv[1]) == "--sidecar") return sidecar_dump(argc, argv);
     if (argc != 6) {
         fprintf(stderr, "Usage: rsem-b200-host-selftest imdName read_type threads seedLen outPrefix\n");
         return -1;

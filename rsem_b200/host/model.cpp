@@ -206,7 +206,7 @@ struct ReadCounts {
 };
 }  // namespace
 
-void HostModel::estimate_from_reads(const std::string& imd, ReadStore& alignable) {
+void HostModel::estimate_from_reads(const std::string& imd, ReadStore& alignable, Sidecar* sc) {
     LenDistH& d = (paired() || has_mld) ? mld : gld;
     d.zero();
     int n_warns = 0;
@@ -217,7 +217,12 @@ void HostModel::estimate_from_reads(const std::string& imd, ReadStore& alignable
         std::vector<std::string> short_names;
         uint64_t n_short = 0;
         const int n_warns_before = n_warns;
-        parse_reads(imd, tag, type, refs->has_polyA, mp.seedLen, rs, &short_names, &n_short);
+        if (sc) {  // already decoded by bin/rsem-parse-alignments (binary side-car): only the lowq flags are derived here
+            rs = std::move(sc->reads[tag]);
+            finish_sidecar_reads(rs, sc->shorts[tag], refs->has_polyA, mp.seedLen, &short_names, &n_short);
+        } else {
+            parse_reads(imd, tag, type, refs->has_polyA, mp.seedLen, rs, &short_names, &n_short);
+        }
         const int T = std::max(1, std::min<int>(g_io_threads, (int)(rs.n / 8192) + 1));
         std::vector<ReadCounts> part(T);
         parallel_ranges((size_t)rs.n, T, [&](size_t b, size_t e, int t) {

@@ -1,6 +1,7 @@
 """Drop-in acceptance test: the UNMODIFIED Perl driver rsem-calculate-expression runs the whole
 pipeline - rsem-parse-alignments, rsem-build-read-index, rsem-run-em (with its default -b posterior BAM and --gibbs-out),
 rsem-run-gibbs - once with the reference's binaries (oracle/_ref) and once with bin/rsem-run-em and bin/rsem-run-gibbs
+(and bin/rsem-parse-alignments, whose binary side-car rsem-run-em then loads instead of parsing .dat and the read files)
 swapped in beside the same driver.  Compared: *.isoforms.results, *.genes.results (EM and posterior-mean columns) and
 every record of *.transcript.bam (MAPQ, ZW tag).  The driver, its module and the reference tools are installed into
 oracle/_ref by oracle/Makefile; nothing is read from /root/reference at run time."""
@@ -23,10 +24,10 @@ def _install(dst, which):
     os.makedirs(dst)
     for f in ("rsem-calculate-expression", "rsem_perl_utils.pm"):
         shutil.copy(os.path.join(rf.REF_DIR, f), dst)       # copies: FindBin::RealBin would follow a symlink back
-    for tool in ("rsem-parse-alignments", "rsem-build-read-index"):
-        os.symlink(os.path.join(rf.REF_DIR, tool), os.path.join(dst, tool))
+    os.symlink(os.path.join(rf.REF_DIR, "rsem-build-read-index"), os.path.join(dst, "rsem-build-read-index"))
     src = rf.REF_DIR if which == "ref" else rf.BIN_DIR
-    for tool in ("rsem-run-em", "rsem-run-gibbs"):
+    # ours: rsem-parse-alignments too - it writes the same text files plus the binary side-car rsem-run-em loads instead
+    for tool in ("rsem-parse-alignments", "rsem-run-em", "rsem-run-gibbs"):
         os.symlink(os.path.join(src, tool), os.path.join(dst, tool))
     return dst
 
@@ -87,6 +88,11 @@ def test_perl_driver_with_our_binaries(installs, name):
     _compare_tables(f"{wo}/smp.genes.results", f"{wr}/smp.genes.results")
     # the intermediate .dat the reference's parser wrote is what gen_dataset predicted (sid sign / strand coordinates)
     assert open(f"{wr}/smp.temp/smp.dat").read().split("\n", 1)[1] == open(f"{data}/s.temp/s.dat").read().split("\n", 1)[1]
+    # our rsem-parse-alignments: the same text files, plus the side-car our rsem-run-em ran from
+    for f in ("smp.dat", "smp.omit"):
+        assert open(f"{wo}/smp.temp/{f}", "rb").read() == open(f"{wr}/smp.temp/{f}", "rb").read(), f
+    assert open(f"{wo}/smp.stat/smp.cnt").read() == open(f"{wr}/smp.stat/smp.cnt").read()
+    assert os.path.getsize(f"{wo}/smp.temp/smp.b200") > 0 and not os.path.exists(f"{wr}/smp.temp/smp.b200")
     tr, rr, ref = read_bam(f"{wr}/smp.transcript.bam")
     to, ro, ours = read_bam(f"{wo}/smp.transcript.bam")
     assert (tr, rr) == (to, ro) and len(ref) == len(ours) > 0
