@@ -19,6 +19,57 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return RSEM_B200_ERR_CUDA;
 }
 
+// ---- device block cache ---------------------------------------------------------------------------------------------
+// RSEM_B200_BLOCK_CACHE=0 turns it off (every request goes to cudaMalloc / cudaFree as before).
+static bool block_cache_on() {
+    static const bool on = !(getenv("RSEM_B200_BLOCK_CACHE") && !strcmp(getenv("RSEM_B200_BLOCK_CACHE"), "0"));
+    return on;
+}
+
+cudaError_t block_alloc(rsem_b200_ctx* ctx, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    if (block_cache_on()) {
+        for (size_t k = 0; k < ctx->idle_blocks.size(); ++k)
+            if (ctx->idle_blocks[k].first == bytes) {
+                *p = ctx->idle_blocks[k].second;
+                ctx->idle_blocks[k] = ctx->idle_blocks.back();
+                ctx->idle_blocks.pop_back();
+                ctx->idle_bytes -= bytes;
+                ctx->live_blocks[*p] = bytes;
+                return cudaSuccess;
+            }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation && !ctx->idle_blocks.empty()) {   // give the cached blocks back and try again
+        cudaGetLastError();
+        block_cache_flush(ctx);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) ctx->live_blocks[*p] = bytes;
+    return e;
+}
+
+void block_free(rsem_b200_ctx* ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->live_blocks.find(p);
+    if (it == ctx->live_blocks.end()) { cudaFree(p); return; }   // not ours (allocated before the cache existed)
+    const size_t bytes = it->second;
+    ctx->live_blocks.erase(it);
+    if (block_cache_on() && bytes >= (1u << 16)) {   // small blocks are not worth keeping
+        ctx->idle_blocks.emplace_back(bytes, p);
+        ctx->idle_bytes += bytes;
+    } else {
+        cudaFree(p);
+    }
+}
+
+void block_cache_flush(rsem_b200_ctx* ctx) {
+    if (!ctx->idle_blocks.empty()) cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->idle_blocks) cudaFree(b.second);
+    ctx->idle_blocks.clear();
+    ctx->idle_bytes = 0;
+}
+
 namespace {
 
 template <class T>
@@ -41,7 +92,7 @@ void free_hits(rsem_b200_ctx* c) {
     if (c->theta_tex) { cudaDestroyTextureObject(c->theta_tex); c->theta_tex = 0; c->theta_tex_ptr = nullptr; }
     if (c->theta) dev_free(c, &c->theta, (size_t)c->M + 1);
     if (c->count) dev_free(c, &c->count, (size_t)c->M + 1);
-    if (c->tile_row) { cudaFree(c->tile_row); c->tile_row = nullptr; }
+    if (c->tile_row) { cudaFree(c->tile_row); c->tile_row = nullptr; }   // small (16 B per ~4000 hits)
     if (c->tile_hit) { cudaFree(c->tile_hit); c->tile_hit = nullptr; }
     if (c->tile_meta) { cudaFree(c->tile_meta); c->tile_meta = nullptr; }
     if (c->wtile_row) { cudaFree(c->wtile_row); c->wtile_row = nullptr; }
@@ -203,6 +254,7 @@ int rsem_b200_ctx_create(int device, rsem_b200_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     RB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    RB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     RB_CUDA(cudaMalloc(&c->done_flag, sizeof(int)));
     RB_CUDA(cudaMalloc(&c->err_flag, sizeof(int)));
@@ -240,6 +292,8 @@ int rsem_b200_ctx_destroy(rsem_b200_ctx* c) {
     cudaFree(c->done_flag);
     cudaFree(c->err_flag);
     for (auto& e : c->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    block_cache_flush(c);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -336,8 +390,15 @@ int rsem_b200_upload_conprb(rsem_b200_ctx* c, const double* conprb, const double
     RB_ARG(c && (conprb || c->H == 0) && (ncpv || c->N == 0), "NULL argument");
     RB_ARG(c->row_ptr, "upload_hits must be called first");
     RB_CUDA(cudaSetDevice(c->device));
-    RB_CUDA(cudaMemcpyAsync(c->conprb, conprb, c->H * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    RB_CUDA(cudaMemcpyAsync(c->ncpv, ncpv, c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // The copies (8 bytes per hit: the bulk of a job's PCIe traffic) go to the copy stream; while they are in flight the
+    // directory of the equivalence-class layout - which depends on row_ptr / sid only - is built on the compute stream.
+    RB_CUDA(cudaStreamSynchronize(c->stream));   // whatever still reads or clears conprb / ncpv
+    RB_CUDA(cudaMemcpyAsync(c->conprb, conprb, c->H * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    RB_CUDA(cudaMemcpyAsync(c->ncpv, ncpv, c->N * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    int rc = em_prepare_frozen_layout(c);
+    const cudaError_t e = cudaStreamSynchronize(c->copy_stream);
+    if (rc) return rc;
+    RB_CUDA(e);
     RB_CUDA(cudaStreamSynchronize(c->stream));
     c->conprb_valid = true;
     c->conprb_epoch++;

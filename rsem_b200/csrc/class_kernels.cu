@@ -684,22 +684,24 @@ __global__ void __launch_bounds__(256) estep_long_rows_kernel(const unsigned lon
 }
 
 // ---- host helpers --------------------------------------------------------------------------------------------------
-struct Scratch {  // frees its buffers on every exit path
+struct Scratch {  // returns its buffers (to the context's block cache) on every exit path
+    rsem_b200_ctx* ctx;
     std::vector<void*> p;
+    explicit Scratch(rsem_b200_ctx* c) : ctx(c) {}
     ~Scratch() {
-        for (void* q : p) cudaFree(q);
+        for (void* q : p) block_free(ctx, q);
     }
     template <class T>
     cudaError_t alloc(T** out, size_t n) {
         void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, (n ? n : 1) * sizeof(T));
+        cudaError_t e = block_alloc(ctx, &q, (n ? n : 1) * sizeof(T));
         if (e == cudaSuccess) p.push_back(q);
         *out = static_cast<T*>(q);
         return e;
     }
     void release(void* q) {
         for (auto& x : p)
-            if (x == q) { cudaFree(q); x = nullptr; }
+            if (x == q) { block_free(ctx, q); x = nullptr; }
     }
     void keep(void* q) {  // ownership moves to the context
         for (auto& x : p)
@@ -734,8 +736,8 @@ struct PhaseTimer {  // RSEM_B200_CLASS_TIMING=1: wall-clock per build phase on 
 
 void class_free(rsem_b200_ctx* ctx) {
     ClassLayout& L = ctx->cls;
-    cudaFree(L.vals); cudaFree(L.ids); cudaFree(L.desc); cudaFree(L.tile); cudaFree(L.batch_first);
-    cudaFree(L.fseg_first); cudaFree(L.rows); cudaFree(L.long_rows); cudaFree(L.cta_ns);
+    block_free(ctx, L.vals); block_free(ctx, L.ids); block_free(ctx, L.desc); block_free(ctx, L.tile); block_free(ctx, L.batch_first);
+    block_free(ctx, L.fseg_first); block_free(ctx, L.rows); block_free(ctx, L.long_rows); block_free(ctx, L.cta_ns);
     L = ClassLayout{};
 }
 
@@ -754,7 +756,7 @@ int class_build(rsem_b200_ctx* ctx) {
         const int v = atoi(e);
         if (v >= 1 && v <= 255) R = (unsigned)v;
     }
-    Scratch sc;
+    Scratch sc(ctx);
     PhaseTimer pt(st);
     // ---- 1. row keys, sorted
     unsigned long long *keys = nullptr, *keys_s = nullptr;
@@ -791,7 +793,7 @@ int class_build(rsem_b200_ctx* ctx) {
     L.n_long = n_long;
     L.n_rows = n_rows;
     if (n_long) {
-        RB_CUDA(cudaMalloc(&L.long_rows, (size_t)n_long * sizeof(unsigned)));
+        RB_CUDA(block_alloc(ctx, reinterpret_cast<void**>(&L.long_rows), (size_t)n_long * sizeof(unsigned)));
         cls_long_rows_kernel<<<blocks_for(n_long, 256), 256, 0, st>>>(keys_s, rows_s, n_rows, n_long, L.long_rows);
         RB_CUDA(cudaGetLastError());
     }
@@ -860,7 +862,7 @@ int class_build(rsem_b200_ctx* ctx) {
     unsigned n_batches = 0;
     RB_CUDA(cudaMemcpyAsync(&n_batches, s_c + (n_segs - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
-    RB_CUDA(cudaMalloc(&L.batch_first, (size_t)n_batches * sizeof(unsigned)));
+    RB_CUDA(block_alloc(ctx, reinterpret_cast<void**>(&L.batch_first), (size_t)n_batches * sizeof(unsigned)));
     cls_batch_scatter_kernel<<<blocks_for(n_segs, 256), 256, 0, st>>>(s_a, s_c, n_segs, L.batch_first);
     RB_CUDA(cudaGetLastError());
     unsigned long long *n_vals = nullptr, *n_ids = nullptr, *val_off = nullptr, *id_off = nullptr;
@@ -894,7 +896,7 @@ int class_build(rsem_b200_ctx* ctx) {
     L.n_ids = totals[1];
     L.n_segs = n_segs;
     L.n_batches = n_batches;
-    RB_CUDA(cudaMalloc(&L.desc, ((size_t)n_batches + 1) * sizeof(BatchDesc)));
+    RB_CUDA(block_alloc(ctx, reinterpret_cast<void**>(&L.desc), ((size_t)n_batches + 1) * sizeof(BatchDesc)));
     cls_batch_desc_kernel<<<blocks_for(n_batches, 256), 256, 0, st>>>(key2_s, L.batch_first, val_off, id_off, same_class, n_batches,
                                                                      n_segs, static_cast<BatchDesc*>(L.desc));
     RB_CUDA(cudaGetLastError());
@@ -923,20 +925,20 @@ int class_build(rsem_b200_ctx* ctx) {
         RB_CUDA(cudaMemcpyAsync(&n_bounds, d_n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         RB_CUDA(cudaStreamSynchronize(st));
         L.n_tiles = (unsigned)(n_bounds - 1);
-        RB_CUDA(cudaMalloc(&L.tile, n_bounds * sizeof(TileRec)));
+        RB_CUDA(block_alloc(ctx, reinterpret_cast<void**>(&L.tile), n_bounds * sizeof(TileRec)));
         cls_tile_rec_kernel<<<blocks_for(n_bounds, 256), 256, 0, st>>>(bound_u, val_off, id_off, n_bounds, static_cast<TileRec*>(L.tile));
         RB_CUDA(cudaGetLastError());
     }
     // ---- 5. what the value gather needs later: first sorted position of every segment in final order + the row order
-    RB_CUDA(cudaMalloc(&L.fseg_first, (size_t)n_segs * sizeof(unsigned)));
+    RB_CUDA(block_alloc(ctx, reinterpret_cast<void**>(&L.fseg_first), (size_t)n_segs * sizeof(unsigned)));
     cls_gather_u32_kernel<<<blocks_for(n_segs, 256), 256, 0, st>>>(seg_first, segid_s, n_segs, L.fseg_first);
     RB_CUDA(cudaGetLastError());
-    RB_CUDA(cudaMalloc(&L.ids, ((size_t)L.n_ids + 64) * sizeof(int)));
+    RB_CUDA(block_alloc(ctx, reinterpret_cast<void**>(&L.ids), ((size_t)L.n_ids + 64) * sizeof(int)));
     RB_CUDA(cudaMemsetAsync(L.ids + L.n_ids, 0, 64 * sizeof(int), st));
     cls_fill_ids_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(rp, sid_abs, static_cast<const BatchDesc*>(L.desc), L.batch_first,
                                                           L.fseg_first, rows_s, n_batches, L.ids);
     RB_CUDA(cudaGetLastError());
-    RB_CUDA(cudaMalloc(&L.vals, ((size_t)L.n_vals + 32) * sizeof(double)));
+    RB_CUDA(block_alloc(ctx, reinterpret_cast<void**>(&L.vals), ((size_t)L.n_vals + 32) * sizeof(double)));
     RB_CUDA(cudaMemsetAsync(L.vals + L.n_vals, 0, 32 * sizeof(double), st));
     RB_CUDA(cudaStreamSynchronize(st));
     pt.mark("tiles, descriptors, ids");
@@ -983,7 +985,7 @@ int class_launch_estep(rsem_b200_ctx* ctx) {
         a.count = ctx->k2_target;
         a.done_flag = ctx->done_flag;
         if (!L.cta_ns) {
-            RB_CUDA(cudaMalloc(&L.cta_ns, (size_t)ctx->sm_count * sizeof(unsigned long long)));
+            RB_CUDA(block_alloc(ctx, reinterpret_cast<void**>(&L.cta_ns), (size_t)ctx->sm_count * sizeof(unsigned long long)));
         }
         a.cta_ns = reinterpret_cast<unsigned long long*>(L.cta_ns);
         unsigned grid = (unsigned)ctx->sm_count;

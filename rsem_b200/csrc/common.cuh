@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/rsem_b200.h"
@@ -152,8 +153,16 @@ struct rsem_b200_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host -> device copies that overlap with work on `stream` (upload_conprb)
     uint64_t launches = 0;
     uint64_t dev_bytes = 0;
+
+    // device block cache (capi.cu: block_alloc / block_free): the buffers of a released hit matrix and of its derived
+    // layouts are kept and handed out again to requests of exactly the same size, so that repeated jobs of one shape pay
+    // neither cudaMalloc nor the device-wide synchronisation of cudaFree.  All users order their work on `stream`.
+    std::vector<std::pair<size_t, void*>> idle_blocks;
+    std::unordered_map<void*, size_t> live_blocks;
+    size_t idle_bytes = 0;
 
     // hit matrix
     uint64_t N = 0, H = 0;
@@ -234,11 +243,16 @@ namespace rsem_b200 {
 
 // allocation with accounting; every array gets 256 B of tail padding so that 16-byte granular
 // bulk copies may over-read the last tile.
+// capi.cu: cached device blocks (see rsem_b200_ctx::idle_blocks)
+cudaError_t block_alloc(rsem_b200_ctx* ctx, void** p, size_t bytes);
+void block_free(rsem_b200_ctx* ctx, void* p);
+void block_cache_flush(rsem_b200_ctx* ctx);
+
 template <class T>
 int dev_alloc(rsem_b200_ctx* ctx, T** p, size_t n) {
     size_t bytes = n * sizeof(T) + 256;
     void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, bytes);
+    cudaError_t e = block_alloc(ctx, &q, bytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
     // the padding is read (never used) by the pair-wise phases of the staged E-step: keep it defined
     cudaMemset(static_cast<char*>(q) + n * sizeof(T), 0, 256);
@@ -249,7 +263,7 @@ int dev_alloc(rsem_b200_ctx* ctx, T** p, size_t n) {
 template <class T>
 void dev_free(rsem_b200_ctx* ctx, T** p, size_t n) {
     if (*p) {
-        cudaFree(*p);
+        block_free(ctx, *p);
         ctx->dev_bytes -= n * sizeof(T) + 256;
         *p = nullptr;
     }
@@ -258,6 +272,7 @@ void dev_free(rsem_b200_ctx* ctx, T** p, size_t n) {
 // em_kernels.cu
 int em_build_tiles(rsem_b200_ctx* ctx);
 int em_launch_estep(rsem_b200_ctx* ctx, bool write_post);
+int em_prepare_frozen_layout(rsem_b200_ctx* ctx);
 int em_launch_theta_update(rsem_b200_ctx* ctx, double n0, int round, int min_round, int max_round, int stats_slot);
 int em_max_degree(rsem_b200_ctx* ctx, uint32_t* max_deg);
 int em_make_abs_sid(rsem_b200_ctx* ctx);

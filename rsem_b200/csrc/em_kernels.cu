@@ -1242,6 +1242,19 @@ int em_build_tiles(rsem_b200_ctx* ctx) {
     return 0;
 }
 
+// frozen-conprb rounds run on the equivalence-class layout unless a CSR variant was selected
+static bool wants_class_layout(const rsem_b200_ctx* ctx) {
+    static const int no_class = getenv("RSEM_B200_NO_CLASS") ? atoi(getenv("RSEM_B200_NO_CLASS")) : 0;
+    return ctx->variant == 5 || (ctx->variant == 0 && !no_class);
+}
+
+// Builds the class directory ahead of the first frozen round (it depends on row_ptr / sid only).  rsem_b200_upload_conprb
+// calls this while the conprb copy is in flight; without it the first em_launch_estep builds the directory itself.
+int em_prepare_frozen_layout(rsem_b200_ctx* ctx) {
+    if (ctx->N == 0 || !wants_class_layout(ctx) || ctx->cls.built) return 0;
+    return class_build(ctx);
+}
+
 int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
     EstepArgs a;
     a.row_ptr = reinterpret_cast<const unsigned long long*>(ctx->row_ptr);
@@ -1287,8 +1300,7 @@ int em_launch_estep(rsem_b200_ctx* ctx, bool write_post) {
     if (ctx->N == 0) return 0;
     // frozen-conprb rounds: equivalence-class layout (class_kernels.cu), built on first use after an upload and
     // re-gathered when conprb changed; posterior write-back stays on the CSR stream (hit order)
-    static const int no_class = getenv("RSEM_B200_NO_CLASS") ? atoi(getenv("RSEM_B200_NO_CLASS")) : 0;
-    if (!write_post && (ctx->variant == 5 || (ctx->variant == 0 && !no_class))) {
+    if (!write_post && wants_class_layout(ctx)) {
         if (!ctx->cls.built) {
             if (int rc = class_build(ctx)) return rc;
         }

@@ -404,8 +404,8 @@ __device__ void generator_loop(const PArgs& a, ChainSync* sy, unsigned* ubuf, un
 //     entries <= u * total (sampling.h:50-65 on a non-decreasing array).
 constexpr int kGL = 16;
 
-struct GroupSmem {
-    double v[kGL];         // products of the current chunk
+struct alignas(16) GroupSmem {
+    double v[kGL];         // products of the current chunk (lanes past the chunk's end store 0.0)
     double al[2 * kGL];    // REG: alpha of the component's local ids
 };
 
@@ -430,15 +430,26 @@ __device__ __forceinline__ void load_head(const PArgs& a, const int* z_prev, con
     r.c = in ? a.p_con[r.off + gl] : 0.0;
 }
 
-// prefix sums of the chunk's products in entry order; lane gl gets arr[base + gl]; returns the running sum after the chunk
+// prefix sums of the chunk's products in entry order; lane gl gets arr[base + gl]; returns the running sum after the chunk.
+// The sum starts from `carry` (0.0 for the first chunk: 0.0 + x == x exactly, so arr[0] is the first product itself as in
+// Gibbs.cpp:286-288) and lanes past the end of the chunk contribute +0.0, which leaves a non-negative sum unchanged: every
+// lane can run the same unrolled sequence of 16-byte shared-memory loads and predicated adds.
 __device__ __forceinline__ double chunk_running_sum(GroupSmem& sm, unsigned gmask, int gl, double v, unsigned base, unsigned n_valid,
                                                     double carry, double& arr) {
+    (void)base;
     sm.v[gl] = v;
     __syncwarp(gmask);
     double run = carry;
-    for (unsigned j = 0; j < n_valid; ++j) {
-        const double x = sm.v[j];
-        if ((int)j <= gl) run = (base + j) ? __dadd_rn(x, run) : x;
+    const double2* p = reinterpret_cast<const double2*>(sm.v);
+#pragma unroll
+    for (int j = 0; j < kGL; j += 4) {
+        if (j < (int)n_valid) {   // group-uniform
+            const double2 a = p[j / 2], b = p[j / 2 + 1];
+            if (j <= gl) run = __dadd_rn(a.x, run);
+            if (j + 1 <= gl) run = __dadd_rn(a.y, run);
+            if (j + 2 <= gl) run = __dadd_rn(b.x, run);
+            if (j + 3 <= gl) run = __dadd_rn(b.y, run);
+        }
     }
     arr = run;
     const double last = __shfl_sync(gmask, run, (int)n_valid - 1, kGL);
@@ -446,21 +457,134 @@ __device__ __forceinline__ double chunk_running_sum(GroupSmem& sm, unsigned gmas
     return last;
 }
 
+// One draw: the sequential part of a row.  `cur` is the row (first chunk of entries in cur.t / cur.c), c0 the noise count it
+// must see.  REG components keep their counts in cnt0 / cnt1 (local ids gl and gl + 16).
 template <bool REG>
-__device__ __forceinline__ void walk_segment(const PArgs& a, int seg, bool use_counts, int* counts, const int* z_prev, int* z_cur,
-                                             const unsigned* u, int c0_start, const unsigned* f_in, unsigned* f_out, const int* pre,
-                                             const int* sh_base, unsigned w_per, unsigned W, int* err, GroupSmem& sm, unsigned gmask, int gl) {
-    const int q0 = a.seg_start[seg], q_end = a.seg_start[seg + 1];
-    const int K = a.seg_ntr[seg];
-    const int* tids = a.comp_tids + a.seg_tid_off[seg];
-    int cnt0 = 0, cnt1 = 0;   // REG: counts of local ids gl and gl + 16
+__device__ __forceinline__ void process_row(const PArgs& a, const RowHead& cur, int q, int c0, bool use_counts, int* counts, int* z_cur,
+                                            unsigned* f_out, unsigned W, int* err, GroupSmem& sm, unsigned gmask, int gl, int& cnt0, int& cnt1) {
+    const double uni = cur.raw * (1.0 / 4294967296.0);
+    const int zo = cur.zo;
+    // value of one entry: (count + alpha) * conprb with the read's own assignment taken out (Gibbs.cpp:298-306)
+    auto entry_value = [&](int t, double c, bool valid, int& cnt_seen) -> double {
+        int cnt = c0;
+        double al;
+        if (REG) {
+            const int src = valid ? (t & (kGL - 1)) : 0;
+            const int x0 = __shfl_sync(gmask, cnt0, src, kGL), x1 = __shfl_sync(gmask, cnt1, src, kGL);
+            if (valid && t != 0) cnt = t < kGL ? x0 : x1;
+            al = sm.al[valid ? t : 0];
+        } else {
+            if (valid && t != 0) cnt = ld_cg(counts + t);
+            al = a.alpha[valid ? t : 0];
+        }
+        if (valid && t == zo) cnt -= 1;
+        cnt_seen = cnt;
+        if (!valid) return 0.0;
+        return use_counts ? __dmul_rn(__dadd_rn((double)cnt, al), c) : c;
+    };
+    int znew;
+    if (cur.len <= (unsigned)kGL) {
+        const bool valid = (unsigned)gl < cur.len;
+        int seen;
+        const double v = entry_value(cur.t, cur.c, valid, seen);
+        double arr;
+        const double total = chunk_running_sum(sm, gmask, gl, v, 0u, cur.len, 0.0, arr);
+        const double prb = __dmul_rn(uni, total);
+        int l = __popc(__ballot_sync(gmask, valid && arr <= prb));
+        if (l >= (int)cur.len) { *err = 3; l = (int)cur.len - 1; }   // reference: assert(l < len), sampling.h:62
+        znew = __shfl_sync(gmask, cur.t, l, kGL);
+        if (!REG && use_counts && znew != zo) {   // the lanes that hold the two entries know the counts they saw
+            if (valid && zo != 0 && cur.t == zo) st_cg(counts + zo, seen);
+            if (gl == l && znew != 0) st_cg(counts + znew, seen + 1);
+        }
+        if (!REG && !use_counts && gl == l && znew != 0) st_cg(counts + znew, ld_cg(counts + znew) + 1);
+    } else {
+        // rows longer than a group: one pass for the total, one for the index
+        double carry = 0.0;
+        for (unsigned base = 0; base < cur.len; base += kGL) {
+            const unsigned k = base + gl, nv = min((unsigned)kGL, cur.len - base);
+            const bool valid = k < cur.len;
+            const int t = valid ? a.p_sid[cur.off + k] : -1;
+            const double c = valid ? a.p_con[cur.off + k] : 0.0;
+            int seen;
+            double arr;
+            carry = chunk_running_sum(sm, gmask, gl, entry_value(t, c, valid, seen), base, nv, carry, arr);
+        }
+        const double prb = __dmul_rn(uni, carry);
+        int l = 0;
+        carry = 0.0;
+        znew = -1;
+        for (unsigned base = 0; base < cur.len; base += kGL) {
+            const unsigned k = base + gl, nv = min((unsigned)kGL, cur.len - base);
+            const bool valid = k < cur.len;
+            const int t = valid ? a.p_sid[cur.off + k] : -1;
+            const double c = valid ? a.p_con[cur.off + k] : 0.0;
+            int seen;
+            double arr;
+            carry = chunk_running_sum(sm, gmask, gl, entry_value(t, c, valid, seen), base, nv, carry, arr);
+            const int below = __popc(__ballot_sync(gmask, valid && arr <= prb));
+            l += below;
+            if (znew < 0 && below < (int)nv) znew = __shfl_sync(gmask, t, below, kGL);   // first entry with arr > prb (group-uniform branch)
+        }
+        if (znew < 0) {   // reference: assert(l < len)
+            *err = 3;
+            znew = a.p_sid[cur.off + cur.len - 1];
+        }
+        if (!REG && gl == 0) {
+            if (use_counts) {
+                if (znew != zo) {
+                    if (zo != 0) st_cg(counts + zo, ld_cg(counts + zo) - 1);
+                    if (znew != 0) st_cg(counts + znew, ld_cg(counts + znew) + 1);
+                }
+            } else if (znew != 0) st_cg(counts + znew, ld_cg(counts + znew) + 1);
+        }
+    }
+    if (REG && znew != zo) {   // owners of the two local ids adjust their registers
+        if (use_counts && zo != 0 && (zo & (kGL - 1)) == gl) { if (zo < kGL) --cnt0; else --cnt1; }
+        if (znew != 0 && (znew & (kGL - 1)) == gl) { if (znew < kGL) ++cnt0; else ++cnt1; }
+    }
+    if (gl == 0) {
+        st_cg(z_cur + q, znew);
+        if (use_counts) {
+            if (zo != 0 && znew == 0) atomicOr(f_out + ((unsigned)cur.i >> 5), 1u << ((unsigned)cur.i & 31u));
+            if (zo == 0 && znew != 0) atomicOr(f_out + W + ((unsigned)cur.i >> 5), 1u << ((unsigned)cur.i & 31u));
+        } else if (znew == 0) atomicAdd(counts, 1);
+    }
+    if (!REG) __syncwarp(gmask);   // the count stores of this read precede the next read's loads (other lanes)
+}
+
+template <bool REG>
+__device__ __forceinline__ void segment_counts_in(const PArgs& a, int seg, int* counts, GroupSmem& sm, unsigned gmask, int gl, int& cnt0, int& cnt1) {
+    cnt0 = cnt1 = 0;
     if (REG) {
+        const int K = a.seg_ntr[seg];
+        const int* tids = a.comp_tids + a.seg_tid_off[seg];
         if (gl >= 1 && gl <= K) cnt0 = ld_cg(counts + tids[gl - 1]);
         if (gl + kGL <= K) cnt1 = ld_cg(counts + tids[gl + kGL - 1]);
         sm.al[gl] = a.alpha[(gl >= 1 && gl <= K) ? tids[gl - 1] : 0];
         sm.al[gl + kGL] = a.alpha[gl + kGL <= K ? tids[gl + kGL - 1] : 0];
         __syncwarp(gmask);
     }
+}
+template <bool REG>
+__device__ __forceinline__ void segment_counts_out(const PArgs& a, int seg, int* counts, int gl, int cnt0, int cnt1) {
+    if (REG) {
+        const int K = a.seg_ntr[seg];
+        const int* tids = a.comp_tids + a.seg_tid_off[seg];
+        if (gl >= 1 && gl <= K) st_cg(counts + tids[gl - 1], cnt0);
+        if (gl + kGL <= K) st_cg(counts + tids[gl + kGL - 1], cnt1);
+    }
+}
+
+// Row-at-a-time walk: the next row's head is loaded while the current one is drawn (prefetch distance 1).  Kept as the
+// cross-check of the pipelined walk below (RSEM_B200_GIBBS_PF=0).
+template <bool REG>
+__device__ __forceinline__ void walk_segment(const PArgs& a, int seg, bool use_counts, int* counts, const int* z_prev, int* z_cur,
+                                             const unsigned* u, int c0_start, const unsigned* f_in, unsigned* f_out, const int* pre,
+                                             const int* sh_base, unsigned w_per, unsigned W, int* err, GroupSmem& sm, unsigned gmask, int gl) {
+    const int q0 = a.seg_start[seg], q_end = a.seg_start[seg + 1];
+    int cnt0, cnt1;
+    segment_counts_in<REG>(a, seg, counts, sm, gmask, gl, cnt0, cnt1);
     RowHead nxt;
     load_head(a, z_prev, u, q0, use_counts, gl, nxt);
     for (int q = q0; q < q_end; ++q) {
@@ -471,103 +595,230 @@ __device__ __forceinline__ void walk_segment(const PArgs& a, int seg, bool use_c
             const unsigned w = (unsigned)cur.i >> 5, m = (1u << ((unsigned)cur.i & 31u)) - 1u;
             c0 += sh_base[w / w_per] + ld_cg(pre + w) + __popc(__ldcg(f_in + w) & m) - __popc(__ldcg(f_in + W + w) & m);
         }
-        const double uni = cur.raw * (1.0 / 4294967296.0);
-        const int zo = cur.zo;
-        // value of one entry: (count + alpha) * conprb with the read's own assignment taken out (Gibbs.cpp:298-306)
-        auto entry_value = [&](int t, double c, bool valid, int& cnt_seen) -> double {
-            int cnt = c0;
-            double al;
-            if (REG) {
-                const int src = valid ? (t & (kGL - 1)) : 0;
-                const int x0 = __shfl_sync(gmask, cnt0, src, kGL), x1 = __shfl_sync(gmask, cnt1, src, kGL);
-                if (valid && t != 0) cnt = t < kGL ? x0 : x1;
-                al = sm.al[valid ? t : 0];
-            } else {
-                if (valid && t != 0) cnt = ld_cg(counts + t);
-                al = a.alpha[valid ? t : 0];
-            }
-            if (valid && t == zo) cnt -= 1;
-            cnt_seen = cnt;
-            if (!valid) return 0.0;
-            return use_counts ? __dmul_rn(__dadd_rn((double)cnt, al), c) : c;
-        };
-        int znew;
-        if (cur.len <= (unsigned)kGL) {
-            const bool valid = (unsigned)gl < cur.len;
-            int seen;
-            const double v = entry_value(cur.t, cur.c, valid, seen);
-            double arr;
-            const double total = chunk_running_sum(sm, gmask, gl, v, 0u, cur.len, 0.0, arr);
-            const double prb = __dmul_rn(uni, total);
-            int l = __popc(__ballot_sync(gmask, valid && arr <= prb));
-            if (l >= (int)cur.len) { *err = 3; l = (int)cur.len - 1; }   // reference: assert(l < len), sampling.h:62
-            znew = __shfl_sync(gmask, cur.t, l, kGL);
-            if (!REG && use_counts && znew != zo) {   // the lanes that hold the two entries know the counts they saw
-                if (valid && zo != 0 && cur.t == zo) st_cg(counts + zo, seen);
-                if (gl == l && znew != 0) st_cg(counts + znew, seen + 1);
-            }
-            if (!REG && !use_counts && gl == l && znew != 0) st_cg(counts + znew, ld_cg(counts + znew) + 1);
-        } else {
-            // rows longer than a group: one pass for the total, one for the index
-            double carry = 0.0;
-            for (unsigned base = 0; base < cur.len; base += kGL) {
-                const unsigned k = base + gl, nv = min((unsigned)kGL, cur.len - base);
-                const bool valid = k < cur.len;
-                const int t = valid ? a.p_sid[cur.off + k] : -1;
-                const double c = valid ? a.p_con[cur.off + k] : 0.0;
-                int seen;
-                double arr;
-                carry = chunk_running_sum(sm, gmask, gl, entry_value(t, c, valid, seen), base, nv, carry, arr);
-            }
-            const double prb = __dmul_rn(uni, carry);
-            int l = 0;
-            carry = 0.0;
-            znew = -1;
-            for (unsigned base = 0; base < cur.len; base += kGL) {
-                const unsigned k = base + gl, nv = min((unsigned)kGL, cur.len - base);
-                const bool valid = k < cur.len;
-                const int t = valid ? a.p_sid[cur.off + k] : -1;
-                const double c = valid ? a.p_con[cur.off + k] : 0.0;
-                int seen;
-                double arr;
-                carry = chunk_running_sum(sm, gmask, gl, entry_value(t, c, valid, seen), base, nv, carry, arr);
-                const int below = __popc(__ballot_sync(gmask, valid && arr <= prb));
-                l += below;
-                if (znew < 0 && below < (int)nv) znew = __shfl_sync(gmask, t, below, kGL);   // first entry with arr > prb (group-uniform branch)
-            }
-            if (znew < 0) {   // reference: assert(l < len)
-                *err = 3;
-                znew = a.p_sid[cur.off + cur.len - 1];
-            }
-            if (!REG && gl == 0) {
-                if (use_counts) {
-                    if (znew != zo) {
-                        if (zo != 0) st_cg(counts + zo, ld_cg(counts + zo) - 1);
-                        if (znew != 0) st_cg(counts + znew, ld_cg(counts + znew) + 1);
-                    }
-                } else if (znew != 0) st_cg(counts + znew, ld_cg(counts + znew) + 1);
-            }
-        }
-        if (REG && znew != zo) {   // owners of the two local ids adjust their registers
-            if (use_counts && zo != 0 && (zo & (kGL - 1)) == gl) { if (zo < kGL) --cnt0; else --cnt1; }
-            if (znew != 0 && (znew & (kGL - 1)) == gl) { if (znew < kGL) ++cnt0; else ++cnt1; }
-        }
-        if (gl == 0) {
-            st_cg(z_cur + q, znew);
-            if (use_counts) {
-                if (zo != 0 && znew == 0) atomicOr(f_out + ((unsigned)cur.i >> 5), 1u << ((unsigned)cur.i & 31u));
-                if (zo == 0 && znew != 0) atomicOr(f_out + W + ((unsigned)cur.i >> 5), 1u << ((unsigned)cur.i & 31u));
-            } else if (znew == 0) atomicAdd(counts, 1);
-        }
-        if (!REG) __syncwarp(gmask);   // the count stores of this read precede the next read's loads (other lanes)
+        process_row<REG>(a, cur, q, c0, use_counts, counts, z_cur, f_out, W, err, sm, gmask, gl, cnt0, cnt1);
     }
-    if (REG) {
-        if (gl >= 1 && gl <= K) st_cg(counts + tids[gl - 1], cnt0);
-        if (gl + kGL <= K) st_cg(counts + tids[gl + kGL - 1], cnt1);
+    segment_counts_out<REG>(a, seg, counts, gl, cnt0, cnt1);
+}
+
+// ---- pipelined walk -------------------------------------------------------------------------------------------------------
+// A walk is one dependent chain per component, so its speed is the latency of one read.  With the row-at-a-time walk that
+// latency is two DRAM round trips (slot -> read id / entry offset -> uniforms, flip words, entries): ~1.5 us per read at
+// 10 M reads.  Here nothing on the chain waits for memory:
+//   * slot metadata (read id, entry offset, length) is loaded 16 slots at a time, one slot per lane, two batches ahead;
+//   * what depends on the read id and is rewritten inside the kernel (the previous assignment, the uniform, the flip words and
+//     their prefix - read through L2, ld.cg) is loaded one batch ahead, again one slot per lane, and handed out by shuffles;
+//   * the entries (ids, conprb: immutable) of the row kPD slots ahead are copied global -> shared with cp.async into a ring of
+//     kPR rows per group; a row is drawn once its copy group has landed (cp.async.wait_group kPD).
+constexpr int kPD = 4;    // rows of entries in flight
+constexpr int kPR = 8;    // ring slots (>= kPD + 2: a slot is rewritten only after every lane has left its row)
+
+struct EntryRing {
+    int t[kPR][kGL];
+    double c[kPR][kGL];
+};
+
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct SlotMeta {   // lane gl: slot qb + gl of a batch
+    int i;                    // read id
+    unsigned len;
+    unsigned long long off;
+};
+struct SlotMut {    // read through L2: rewritten by other CTAs between sweeps / passes
+    int z;
+    unsigned raw;
+    int pre;
+    unsigned f0, f1;
+};
+
+__device__ __forceinline__ void load_meta(const PArgs& a, int q, int q_end, SlotMeta& m) {
+    m.i = 0; m.len = 0; m.off = 0;
+    if (q < q_end) {
+        m.i = __ldg(a.order + q);
+        m.off = __ldg(a.p_off + q);
+        m.len = (unsigned)(__ldg(a.p_off + q + 1) - m.off);
+    }
+}
+__device__ __forceinline__ void load_mut(const SlotMeta& m, int q, int q_end, bool use_counts, const int* z_prev, const unsigned* u,
+                                         const unsigned* f_in, const int* pre, unsigned W, SlotMut& x) {
+    x.z = 0; x.raw = 0; x.pre = 0; x.f0 = 0; x.f1 = 0;
+    if (q < q_end) {
+        x.raw = __ldcg(u + m.i);
+        if (use_counts) {
+            const unsigned w = (unsigned)m.i >> 5;
+            x.z = ld_cg(z_prev + q);
+            x.pre = ld_cg(pre + w);
+            x.f0 = __ldcg(f_in + w);
+            x.f1 = __ldcg(f_in + W + w);
+        }
+    }
+}
+// net flips of the input set before read i (the noise count read i must see, minus c0 at the start of the sweep)
+__device__ __forceinline__ int noise_adjust(const SlotMeta& m, const SlotMut& x, const int* sh_base, unsigned w_per) {
+    const unsigned w = (unsigned)m.i >> 5, msk = (1u << ((unsigned)m.i & 31u)) - 1u;
+    return sh_base[w / w_per] + x.pre + __popc(x.f0 & msk) - __popc(x.f1 & msk);
+}
+
+template <bool REG>
+__device__ __forceinline__ void walk_segment_pf(const PArgs& a, int seg, bool use_counts, int* counts, const int* z_prev, int* z_cur,
+                                                const unsigned* u, int c0_start, const unsigned* f_in, unsigned* f_out, const int* pre,
+                                                const int* sh_base, unsigned w_per, unsigned W, int* err, GroupSmem& sm, EntryRing& ring,
+                                                unsigned gmask, int gl) {
+    const int q0 = a.seg_start[seg], q_end = a.seg_start[seg + 1];
+    const int n = q_end - q0;
+    int cnt0, cnt1;
+    segment_counts_in<REG>(a, seg, counts, sm, gmask, gl, cnt0, cnt1);
+    SlotMeta m0, m1, m2;   // batches b, b + 1, b + 2 of 16 slots
+    load_meta(a, q0 + gl, q_end, m0);
+    load_meta(a, q0 + kGL + gl, q_end, m1);
+    load_meta(a, q0 + 2 * kGL + gl, q_end, m2);
+    SlotMut x0, x1;        // batches b, b + 1
+    load_mut(m0, q0 + gl, q_end, use_counts, z_prev, u, f_in, pre, W, x0);
+    load_mut(m1, q0 + kGL + gl, q_end, use_counts, z_prev, u, f_in, pre, W, x1);
+    int adj0 = use_counts ? noise_adjust(m0, x0, sh_base, w_per) : 0;
+    // row r of the segment lives in batch r / 16; while row r0 of batch b is drawn, rows up to r0 + kPD are fetched: they are
+    // in batch b (m0) or b + 1 (m1)
+    auto fetch = [&](int r, bool next_batch) {
+        const int lr = r & (kGL - 1);
+        const unsigned long long off = __shfl_sync(gmask, next_batch ? m1.off : m0.off, lr, kGL);
+        const unsigned len = __shfl_sync(gmask, next_batch ? m1.len : m0.len, lr, kGL);
+        if (r < n && (unsigned)gl < len) {
+            const int s = r & (kPR - 1);
+            cp_async_4(&ring.t[s][gl], a.p_sid + off + gl);
+            cp_async_8(&ring.c[s][gl], a.p_con + off + gl);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int d = 0; d < kPD; ++d) fetch(d, false);
+    for (int r = 0; r < n; ++r) {
+        const int lr = r & (kGL - 1);
+        if (lr == 0 && r > 0) {   // next batch: rotate, start the loads of the batches after it
+            m0 = m1; m1 = m2;
+            load_meta(a, q0 + r + 2 * kGL + gl, q_end, m2);
+            x0 = x1;
+            adj0 = use_counts ? noise_adjust(m0, x0, sh_base, w_per) : 0;
+            load_mut(m1, q0 + r + kGL + gl, q_end, use_counts, z_prev, u, f_in, pre, W, x1);
+        }
+        fetch(r + kPD, lr + kPD >= kGL);
+        cp_async_wait<kPD>();
+        __syncwarp(gmask);
+        RowHead cur;
+        cur.i = __shfl_sync(gmask, m0.i, lr, kGL);
+        cur.len = __shfl_sync(gmask, m0.len, lr, kGL);
+        cur.off = __shfl_sync(gmask, m0.off, lr, kGL);
+        cur.zo = __shfl_sync(gmask, x0.z, lr, kGL);
+        cur.raw = __shfl_sync(gmask, x0.raw, lr, kGL);
+        const int c0 = c0_start + __shfl_sync(gmask, adj0, lr, kGL);
+        const bool in = (unsigned)gl < cur.len;
+        const int s = r & (kPR - 1);
+        cur.t = in ? ring.t[s][gl] : -1;
+        cur.c = in ? ring.c[s][gl] : 0.0;
+        process_row<REG>(a, cur, q0 + r, c0, use_counts, counts, z_cur, f_out, W, err, sm, gmask, gl, cnt0, cnt1);
+    }
+    cp_async_wait<0>();
+    __syncwarp(gmask);   // every lane has left the ring before the group's next segment refills it
+    segment_counts_out<REG>(a, seg, counts, gl, cnt0, cnt1);
+}
+
+// ---- one pass, both lane groups of a warp in ONE loop ---------------------------------------------------------------------
+// With a walk function per segment the two groups of a warp fall out of step at the first segment boundary and from then on
+// every instruction is issued twice, once per half-warp, the two dependent chains taking turns on one instruction stream.
+// Here a warp runs a single loop over "the current row of each group"; claiming the next component and priming its pipeline
+// is a short divergent section, the draw itself is issued once for both groups.
+__device__ __forceinline__ void walk_pass_converged(const PArgs& a, ChainSync* sy, bool use_counts, int* counts, const int* z_prev,
+                                                    int* z_cur, const unsigned* u, int c0_start, const unsigned* f_in, unsigned* f_out,
+                                                    const int* pre, const int* sh_base, unsigned w_per, unsigned W, GroupSmem& sm,
+                                                    EntryRing& ring, unsigned gmask, int gl) {
+    int seg = -1, q0 = 0, q_end = 0, n = 0, r = 0;
+    bool active = true, reg = true;
+    int cnt0 = 0, cnt1 = 0, adj0 = 0;
+    SlotMeta m0, m1, m2;
+    SlotMut x0, x1;
+    m0.i = m1.i = m2.i = 0; m0.len = m1.len = m2.len = 0; m0.off = m1.off = m2.off = 0;
+    x0.z = x1.z = 0; x0.raw = x1.raw = 0; x0.pre = x1.pre = 0; x0.f0 = x1.f0 = 0; x0.f1 = x1.f1 = 0;
+    auto fetch = [&](int rr, bool next_batch) {
+        const int lr = rr & (kGL - 1);
+        const unsigned long long off = __shfl_sync(gmask, next_batch ? m1.off : m0.off, lr, kGL);
+        const unsigned len = __shfl_sync(gmask, next_batch ? m1.len : m0.len, lr, kGL);
+        if (rr < n && (unsigned)gl < len) {
+            const int sl = rr & (kPR - 1);
+            cp_async_4(&ring.t[sl][gl], a.p_sid + off + gl);
+            cp_async_8(&ring.c[sl][gl], a.p_con + off + gl);
+        }
+        cp_async_commit();
+    };
+    for (;;) {
+        if (active && r == n) {   // group-divergent: finish the component, claim the next one, prime its pipeline
+            if (seg >= 0) {
+                cp_async_wait<0>();
+                __syncwarp(gmask);   // every lane has left the ring
+                if (reg) segment_counts_out<true>(a, seg, counts, gl, cnt0, cnt1);
+            }
+            int sgm = 0;
+            if (gl == 0) sgm = (int)atomicAdd(&sy->next_seg, 1u);
+            sgm = __shfl_sync(gmask, sgm, 0, kGL);
+            if (sgm >= a.n_segs) active = false;
+            else {
+                seg = sgm;
+                q0 = a.seg_start[seg];
+                q_end = a.seg_start[seg + 1];
+                n = q_end - q0;
+                r = 0;
+                reg = a.seg_ntr[seg] < 2 * kGL;
+                if (reg) segment_counts_in<true>(a, seg, counts, sm, gmask, gl, cnt0, cnt1);
+                load_meta(a, q0 + gl, q_end, m0);
+                load_meta(a, q0 + kGL + gl, q_end, m1);
+                load_meta(a, q0 + 2 * kGL + gl, q_end, m2);
+                load_mut(m0, q0 + gl, q_end, use_counts, z_prev, u, f_in, pre, W, x0);
+                load_mut(m1, q0 + kGL + gl, q_end, use_counts, z_prev, u, f_in, pre, W, x1);
+                adj0 = use_counts ? noise_adjust(m0, x0, sh_base, w_per) : 0;
+#pragma unroll
+                for (int d = 0; d < kPD; ++d) fetch(d, false);
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;   // both groups of the warp are here in every iteration
+        if (active) {
+            const int lr = r & (kGL - 1);
+            if (lr == 0 && r > 0) {   // next batch of 16 slots: rotate, start the loads of the batches after it
+                m0 = m1; m1 = m2;
+                load_meta(a, q0 + r + 2 * kGL + gl, q_end, m2);
+                x0 = x1;
+                adj0 = use_counts ? noise_adjust(m0, x0, sh_base, w_per) : 0;
+                load_mut(m1, q0 + r + kGL + gl, q_end, use_counts, z_prev, u, f_in, pre, W, x1);
+            }
+            fetch(r + kPD, lr + kPD >= kGL);
+            cp_async_wait<kPD>();
+            __syncwarp(gmask);
+            RowHead cur;
+            cur.i = __shfl_sync(gmask, m0.i, lr, kGL);
+            cur.len = __shfl_sync(gmask, m0.len, lr, kGL);
+            cur.off = __shfl_sync(gmask, m0.off, lr, kGL);
+            cur.zo = __shfl_sync(gmask, x0.z, lr, kGL);
+            cur.raw = __shfl_sync(gmask, x0.raw, lr, kGL);
+            const int c0 = c0_start + __shfl_sync(gmask, adj0, lr, kGL);
+            const bool in = (unsigned)gl < cur.len;
+            const int sl = r & (kPR - 1);
+            cur.t = in ? ring.t[sl][gl] : -1;
+            cur.c = in ? ring.c[sl][gl] : 0.0;
+            if (reg) process_row<true>(a, cur, q0 + r, c0, use_counts, counts, z_cur, f_out, W, &sy->err, sm, gmask, gl, cnt0, cnt1);
+            else process_row<false>(a, cur, q0 + r, c0, use_counts, counts, z_cur, f_out, W, &sy->err, sm, gmask, gl, cnt0, cnt1);
+            ++r;
+        }
     }
 }
 
-__global__ void __launch_bounds__(kPThreads, 4) gibbs_parallel_kernel(const PArgs a) {
+template <int PF>   // 0: row-at-a-time walk, 1: pipelined walk per segment, 2: pipelined, both groups of a warp in one loop
+__global__ void __launch_bounds__(kPThreads, PF ? 3 : 4) gibbs_parallel_kernel(const PArgs a) {
+    __shared__ EntryRing sh_ring[PF ? kPThreads / kGL : 1];
     __shared__ double sh_red[kPThreads / 32];
     __shared__ int sh_scan[kPThreads];
     __shared__ int sh_base[512];     // exclusive prefix of the slice totals (<= 512 worker CTAs per chain)
@@ -653,12 +904,24 @@ __global__ void __launch_bounds__(kPThreads, 4) gibbs_parallel_kernel(const PArg
                 const int gl = tid & (kGL - 1);
                 const unsigned gmask = 0xffffu << ((tid & 31) & ~(kGL - 1));
                 GroupSmem& gsm = sh_grp[tid / kGL];
+                if (PF == 2) {
+                    walk_pass_converged(a, sy, use_counts, counts, z_prev, z_cur, u, c0_start, f_in, f_out, pre, sh_base, w_per, W, gsm,
+                                        sh_ring[PF ? tid / kGL : 0], gmask, gl);
+                } else
                 for (;;) {
                     int sgm = 0;
                     if (gl == 0) sgm = (int)atomicAdd(&sy->next_seg, 1u);
                     sgm = __shfl_sync(gmask, sgm, 0, kGL);
                     if (sgm >= a.n_segs) break;
-                    if (a.seg_ntr[sgm] < 2 * kGL)
+                    if (PF) {
+                        EntryRing& ring = sh_ring[PF ? tid / kGL : 0];
+                        if (a.seg_ntr[sgm] < 2 * kGL)
+                            walk_segment_pf<true>(a, sgm, use_counts, counts, z_prev, z_cur, u, c0_start, f_in, f_out, pre, sh_base, w_per, W,
+                                                  &sy->err, gsm, ring, gmask, gl);
+                        else
+                            walk_segment_pf<false>(a, sgm, use_counts, counts, z_prev, z_cur, u, c0_start, f_in, f_out, pre, sh_base, w_per, W,
+                                                   &sy->err, gsm, ring, gmask, gl);
+                    } else if (a.seg_ntr[sgm] < 2 * kGL)
                         walk_segment<true>(a, sgm, use_counts, counts, z_prev, z_cur, u, c0_start, f_in, f_out, pre, sh_base, w_per, W, &sy->err,
                                            gsm, gmask, gl);
                     else
@@ -1022,8 +1285,13 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
 
     // co-resident CTAs: chains run in waves, every chain gets the same number of worker CTAs (one thread per component
     // is all the parallelism a sweep has) + 1 generator CTA
+    // RSEM_B200_GIBBS_PF: 2 (default) pipelined walk with both lane groups of a warp in one loop, 1 pipelined walk per
+    // segment, 0 row-at-a-time walk (prefetch distance 1); 0 and 1 are kept as cross-checks
+    const char* pf_env = getenv("RSEM_B200_GIBBS_PF");
+    const int pf = pf_env ? std::max(0, std::min(2, atoi(pf_env))) : 2;
+    void* kernel = pf == 2 ? (void*)gibbs_parallel_kernel<2> : pf == 1 ? (void*)gibbs_parallel_kernel<1> : (void*)gibbs_parallel_kernel<0>;
     int per_sm = 0;
-    RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_parallel_kernel, kPThreads, 0));
+    RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void (*)(const PArgs))kernel, kPThreads, 0));
     const int resident = std::max(1, per_sm) * c->sm_count;
     int ctas = std::max(1, std::min(512, (g.n_segs * kGL + kPThreads - 1) / kPThreads));
     if (const char* e = getenv("RSEM_B200_GIBBS_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 512) ctas = v; }
@@ -1076,7 +1344,7 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
         a.chain_base = base;
         a.ctas_per_chain = ctas;
         void* kargs[] = {(void*)&a};
-        RB_TRYC(cudaLaunchCooperativeKernel((void*)gibbs_parallel_kernel, dim3(wave * (ctas + 1)), dim3(kPThreads), kargs, 0, c->stream));
+        RB_TRYC(cudaLaunchCooperativeKernel(kernel, dim3(wave * (ctas + 1)), dim3(kPThreads), kargs, 0, c->stream));
         c->launches++;
     }
     std::vector<double> h_acc((size_t)nc * acc_per);

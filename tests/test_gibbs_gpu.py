@@ -109,3 +109,66 @@ def test_chains_match_oracle(ctx, oracle, mode, noise_scale, block, monkeypatch)
     # the noise count really moves in the stressed cases (otherwise the roll-back path is not exercised)
     if noise_scale >= 1.0:
         assert len(set(cv[:, 0].tolist())) > 1
+
+
+def _family_matrix(N, M, seed, max_family, junk):
+    """disjoint isoform families (one connected component each; <= 31 transcripts: register-resident counts, more: counts
+    in L2), reads hit a run of members of one family, the noise entry first; a few rows longer than 16 entries"""
+    rng = np.random.default_rng(seed)
+    sizes, tot = [], 0
+    while tot < M:
+        k = min(int(rng.integers(1, max_family + 1)), M - tot)
+        sizes.append(k)
+        tot += k
+    sizes = np.array(sizes)
+    start = np.concatenate([[1], 1 + np.cumsum(sizes)[:-1]])
+    wgt = rng.random(len(sizes)) ** 3 + 1e-3
+    fam = rng.choice(len(sizes), size=N, p=wgt / wgt.sum())
+    rows_sid, rows_val, rp = [], [], [0]
+    for i in range(N):
+        k = int(sizes[fam[i]])
+        d = k if rng.random() < 0.7 else int(rng.integers(1, k + 1))
+        first = int(start[fam[i]]) + int(rng.integers(0, k - d + 1))
+        s = [0] + list(range(first, first + d))
+        v = list(10.0 ** rng.uniform(-12, -3, d))
+        nz = 10.0 ** rng.uniform(-14, -5, 1)[0] if rng.random() < junk else 10.0 ** rng.uniform(-60, -40, 1)[0]
+        if rng.random() < 0.05:   # a row without a noise entry
+            s, v = s[1:], v
+        else:
+            v = [nz] + v
+        rows_sid += s
+        rows_val += v
+        rp.append(len(rows_sid))
+    return np.array(rp, np.uint64), np.array(rows_sid, np.int32), np.array(rows_val, np.float64)
+
+
+@pytest.mark.parametrize("pf", ["2", "1", "0"])
+@pytest.mark.parametrize("max_family,junk", [(12, 0.02), (40, 0.3)])
+def test_family_components_match_oracle(ctx, oracle, pf, max_family, junk, monkeypatch):
+    """the component walk of the parallel sampler (RSEM_B200_GIBBS_PF = 2 pipelined + converged, 1 pipelined per segment, 0 row-at-a-time) on the matrix shape
+    it is built for: many components of very different sizes, segments of hundreds of rows (many 16-slot batches),
+    rows that fill a lane group exactly and rows longer than one"""
+    N, M = 30000, 1500
+    rp, sid, val = _family_matrix(N, M, seed=max_family, max_family=max_family, junk=junk)
+    n0 = 1500.0
+    init = np.zeros(M + 1, np.int32)
+    alpha = np.ones(M + 1)
+    totc = (M + 1) * 1.0 + n0 + N
+    rng = np.random.default_rng(2)
+    eel = np.concatenate([[0.0], rng.uniform(200, 2000, M)])
+    mw = np.ones(M + 1)
+    genes = np.arange(1, M + 2, 4, dtype=np.int32)
+    genes[-1] = M + 1
+    samples, burnin, gap = [2, 2], 3, 1
+    seeds = oracle.chain_seeds(7, 2)
+    monkeypatch.setenv("RSEM_B200_GIBBS", "parallel")
+    monkeypatch.setenv("RSEM_B200_GIBBS_PF", pf)
+    cv, sums = _run_gpu(ctx, rp, sid, val, M, n0, init, alpha, totc, eel, mw, genes, burnin, gap, samples, seeds)
+    at = 0
+    for t, ns in enumerate(samples):
+        cv_ref, _ = oracle.gibbs_chain(rp, sid, val, M, n0, init, alpha, totc, eel, mw, genes, burnin, gap, ns, int(seeds[t]))
+        assert np.array_equal(cv[at:at + ns], cv_ref), f"chain {t} differs"
+        at += ns
+    assert len(set(cv[:, 0].tolist())) > 1   # reads do move in and out of the noise transcript
+    lens = np.diff(rp.astype(np.int64))
+    assert lens.max() > 16 or max_family <= 12
