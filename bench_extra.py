@@ -116,8 +116,10 @@ def run_gibbs(args):
     run(2, 1)  # warm-up (allocations, first launch)
     W = max(args.warmup, 3)
     K = args.steps
-    t_short = run(W, 1)          # W + 1 sweeps per chain
-    t_long = run(W, 1 + K)       # W + 1 + K sweeps per chain: the difference times exactly K sweeps (x chains)
+    # W + 1 sweeps per chain, then W + 1 + K: the difference times exactly K sweeps (x chains) through the whole C-ABI call;
+    # each twice, the faster one counts (allocation / first-touch noise of a call is of the order of 0.1 s)
+    t_short = min(run(W, 1), run(W, 1))
+    t_long = min(run(W, 1 + K), run(W, 1 + K))
     per_sweep_all = (t_long - t_short) / K          # one sweep of all chains, seconds
     chain_sweeps_per_s = chains / per_sweep_all
     # bytes per chain-sweep when C chains share the stream = (12 E + 8 N) / C + 8 N

@@ -291,6 +291,7 @@ struct PArgs {
     const int* seg_tid_off;             // offset of the component's sorted transcript ids in comp_tids
     const int* comp_tids;
     int n_segs;
+    int fast_rows;                      // converged walk: lean code path for rows of register-resident components
     int M, burnin, gap, n_genes, n_chains, ctas_per_chain, chain_base;
     const int* chain_samples;
     const unsigned* chain_seeds;
@@ -406,6 +407,7 @@ constexpr int kGL = 16;
 
 struct alignas(16) GroupSmem {
     double v[kGL];         // products of the current chunk (lanes past the chunk's end store 0.0)
+    double w[2][2 * kGL];  // fast path of the converged walk: products of rows r, r + 1 (double-buffered: one __syncwarp per row)
     double al[2 * kGL];    // REG: alpha of the component's local ids
 };
 
@@ -609,12 +611,13 @@ __device__ __forceinline__ void walk_segment(const PArgs& a, int seg, bool use_c
 //     their prefix - read through L2, ld.cg) is loaded one batch ahead, again one slot per lane, and handed out by shuffles;
 //   * the entries (ids, conprb: immutable) of the row kPD slots ahead are copied global -> shared with cp.async into a ring of
 //     kPR rows per group; a row is drawn once its copy group has landed (cp.async.wait_group kPD).
-constexpr int kPD = 4;    // rows of entries in flight
-constexpr int kPR = 8;    // ring slots (>= kPD + 2: a slot is rewritten only after every lane has left its row)
+constexpr int kPD = 2;    // rows of entries in flight
+constexpr int kPR = 4;    // ring slots (>= kPD + 2: a slot is rewritten only after every lane has left its row)
+constexpr int kPE = 2 * kGL;   // entries of a row kept in the ring (two per lane); longer rows read the rest from global memory
 
 struct EntryRing {
-    int t[kPR][kGL];
-    double c[kPR][kGL];
+    int t[kPR][kPE];
+    double c[kPR][kPE];
 };
 
 __device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
@@ -729,6 +732,73 @@ __device__ __forceinline__ void walk_segment_pf(const PArgs& a, int seg, bool us
     segment_counts_out<REG>(a, seg, counts, gl, cnt0, cnt1);
 }
 
+// The draw of a row of <= 16 entries of a register-resident component with live counts (every sweep but the first) - the
+// case almost every read is - written for the shortest dependent chain: the running sum is a chain of DADDs only (terms past
+// the lane's own index enter as +0.0, which leaves a non-negative sum unchanged), the product buffer is double-buffered so
+// that a row needs one __syncwarp, and nothing that is only needed when the read changes its noise membership is computed
+// up front.  Same arithmetic as process_row<true>: (count + alpha) * conprb, left-to-right fp64 sums, index = #{arr <= u * total}.
+__device__ __forceinline__ double reg_entry_value(const GroupSmem& sm, unsigned gmask, bool valid, int t, double c, int zo, int c0,
+                                                  int cnt0, int cnt1) {
+    const int x0 = __shfl_sync(gmask, cnt0, t & (kGL - 1), kGL), x1 = __shfl_sync(gmask, cnt1, t & (kGL - 1), kGL);
+    int cnt = (t & kGL) ? x1 : x0;
+    if (t == 0) cnt = c0;
+    if (t == zo) cnt -= 1;
+    const double al = sm.al[valid ? t : 0];
+    return valid ? __dmul_rn(__dadd_rn((double)cnt, al), c) : 0.0;
+}
+
+// Rows of up to 32 entries: lane gl owns entries gl and gl + 16.  The second half continues the first half's sum:
+// arr[gl + 16] = ((x_0 + ... + x_15) + x_16 + ... + x_{gl+16}), all in entry order.
+__device__ __forceinline__ int draw_reg_row(GroupSmem& sm, int buf, unsigned gmask, int gl, int len, int zo, unsigned raw, int c0, int t0,
+                                            double c0v, int t1, double c1v, int& cnt0, int& cnt1, int* err) {
+    const bool two = len > kGL;   // group-uniform
+    const bool valid0 = gl < len, valid1 = gl + kGL < len;
+    sm.w[buf][gl] = reg_entry_value(sm, gmask, valid0, t0, c0v, zo, c0, cnt0, cnt1);
+    if (two) sm.w[buf][gl + kGL] = reg_entry_value(sm, gmask, valid1, t1, c1v, zo, c0, cnt0, cnt1);
+    __syncwarp(gmask);
+    const double2* p = reinterpret_cast<const double2*>(sm.w[buf]);
+    double run0 = 0.0, run1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < kGL; j += 4) {
+        if (j < len) {   // group-uniform
+            const double2 A = p[j / 2], B = p[j / 2 + 1];
+            run0 = __dadd_rn(j <= gl ? A.x : 0.0, run0);
+            run0 = __dadd_rn(j + 1 <= gl ? A.y : 0.0, run0);
+            run0 = __dadd_rn(j + 2 <= gl ? B.x : 0.0, run0);
+            run0 = __dadd_rn(j + 3 <= gl ? B.y : 0.0, run0);
+            if (two) {       // the sum of the whole first half, the same in every lane
+                run1 = __dadd_rn(A.x, run1);
+                run1 = __dadd_rn(A.y, run1);
+                run1 = __dadd_rn(B.x, run1);
+                run1 = __dadd_rn(B.y, run1);
+            }
+        }
+    }
+    if (two) {
+#pragma unroll
+        for (int j = 0; j < kGL; j += 4) {
+            if (j + kGL < len) {
+                const double2 A = p[(j + kGL) / 2], B = p[(j + kGL) / 2 + 1];
+                run1 = __dadd_rn(j <= gl ? A.x : 0.0, run1);
+                run1 = __dadd_rn(j + 1 <= gl ? A.y : 0.0, run1);
+                run1 = __dadd_rn(j + 2 <= gl ? B.x : 0.0, run1);
+                run1 = __dadd_rn(j + 3 <= gl ? B.y : 0.0, run1);
+            }
+        }
+    }
+    const double total = two ? __shfl_sync(gmask, run1, len - 1 - kGL, kGL) : __shfl_sync(gmask, run0, len - 1, kGL);
+    const double prb = __dmul_rn(raw * (1.0 / 4294967296.0), total);
+    int l = __popc(__ballot_sync(gmask, valid0 && run0 <= prb));
+    if (two) l += __popc(__ballot_sync(gmask, valid1 && run1 <= prb));
+    if (l >= len) { *err = 3; l = len - 1; }   // reference: assert(l < len), sampling.h:62
+    const int znew = l < kGL ? __shfl_sync(gmask, t0, l, kGL) : __shfl_sync(gmask, t1, l - kGL, kGL);
+    if (znew != zo) {   // owners of the two local ids adjust their registers
+        if (zo != 0 && (zo & (kGL - 1)) == gl) { if (zo < kGL) --cnt0; else --cnt1; }
+        if (znew != 0 && (znew & (kGL - 1)) == gl) { if (znew < kGL) ++cnt0; else ++cnt1; }
+    }
+    return znew;
+}
+
 // ---- one pass, both lane groups of a warp in ONE loop ---------------------------------------------------------------------
 // With a walk function per segment the two groups of a warp fall out of step at the first segment boundary and from then on
 // every instruction is issued twice, once per half-warp, the two dependent chains taking turns on one instruction stream.
@@ -749,10 +819,16 @@ __device__ __forceinline__ void walk_pass_converged(const PArgs& a, ChainSync* s
         const int lr = rr & (kGL - 1);
         const unsigned long long off = __shfl_sync(gmask, next_batch ? m1.off : m0.off, lr, kGL);
         const unsigned len = __shfl_sync(gmask, next_batch ? m1.len : m0.len, lr, kGL);
-        if (rr < n && (unsigned)gl < len) {
+        if (rr < n) {
             const int sl = rr & (kPR - 1);
-            cp_async_4(&ring.t[sl][gl], a.p_sid + off + gl);
-            cp_async_8(&ring.c[sl][gl], a.p_con + off + gl);
+            if ((unsigned)gl < len) {
+                cp_async_4(&ring.t[sl][gl], a.p_sid + off + gl);
+                cp_async_8(&ring.c[sl][gl], a.p_con + off + gl);
+            }
+            if ((unsigned)gl + kGL < len) {
+                cp_async_4(&ring.t[sl][gl + kGL], a.p_sid + off + gl + kGL);
+                cp_async_8(&ring.c[sl][gl + kGL], a.p_con + off + gl + kGL);
+            }
         }
         cp_async_commit();
     };
@@ -798,19 +874,37 @@ __device__ __forceinline__ void walk_pass_converged(const PArgs& a, ChainSync* s
             fetch(r + kPD, lr + kPD >= kGL);
             cp_async_wait<kPD>();
             __syncwarp(gmask);
-            RowHead cur;
-            cur.i = __shfl_sync(gmask, m0.i, lr, kGL);
-            cur.len = __shfl_sync(gmask, m0.len, lr, kGL);
-            cur.off = __shfl_sync(gmask, m0.off, lr, kGL);
-            cur.zo = __shfl_sync(gmask, x0.z, lr, kGL);
-            cur.raw = __shfl_sync(gmask, x0.raw, lr, kGL);
+            const int len = (int)__shfl_sync(gmask, m0.len, lr, kGL);
+            const int zo = __shfl_sync(gmask, x0.z, lr, kGL);
+            const unsigned raw = __shfl_sync(gmask, x0.raw, lr, kGL);
             const int c0 = c0_start + __shfl_sync(gmask, adj0, lr, kGL);
-            const bool in = (unsigned)gl < cur.len;
+            const bool in = gl < len;
             const int sl = r & (kPR - 1);
-            cur.t = in ? ring.t[sl][gl] : -1;
-            cur.c = in ? ring.c[sl][gl] : 0.0;
-            if (reg) process_row<true>(a, cur, q0 + r, c0, use_counts, counts, z_cur, f_out, W, &sy->err, sm, gmask, gl, cnt0, cnt1);
-            else process_row<false>(a, cur, q0 + r, c0, use_counts, counts, z_cur, f_out, W, &sy->err, sm, gmask, gl, cnt0, cnt1);
+            const int t = in ? ring.t[sl][gl] : -1;
+            const double c = in ? ring.c[sl][gl] : 0.0;
+            if (a.fast_rows && reg && use_counts && len <= kPE) {
+                const bool in1 = gl + kGL < len;
+                const int t1 = in1 ? ring.t[sl][gl + kGL] : -1;
+                const double c1 = in1 ? ring.c[sl][gl + kGL] : 0.0;
+                const int znew = draw_reg_row(sm, r & 1, gmask, gl, len, zo, raw, c0, t, c, t1, c1, cnt0, cnt1, &sy->err);
+                if (gl == 0) st_cg(z_cur + q0 + r, znew);
+                if ((zo == 0) != (znew == 0)) {   // the read joined or left the noise transcript (group-uniform, rare)
+                    const unsigned i = (unsigned)__shfl_sync(gmask, m0.i, lr, kGL);
+                    if (gl == 0) atomicOr(f_out + (znew == 0 ? 0u : W) + (i >> 5), 1u << (i & 31u));
+                }
+            } else {
+                __syncwarp(gmask);   // a fast row may still be read from sm.w by a slower lane; sm.v is separate, but keep rows apart
+                RowHead cur;
+                cur.i = __shfl_sync(gmask, m0.i, lr, kGL);
+                cur.len = (unsigned)len;
+                cur.off = __shfl_sync(gmask, m0.off, lr, kGL);
+                cur.zo = zo;
+                cur.raw = raw;
+                cur.t = t;
+                cur.c = c;
+                if (reg) process_row<true>(a, cur, q0 + r, c0, use_counts, counts, z_cur, f_out, W, &sy->err, sm, gmask, gl, cnt0, cnt1);
+                else process_row<false>(a, cur, q0 + r, c0, use_counts, counts, z_cur, f_out, W, &sy->err, sm, gmask, gl, cnt0, cnt1);
+            }
             ++r;
         }
     }
@@ -1339,6 +1433,13 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
     a.ubuf = d_u; a.flips = d_flips; a.pre = d_pre; a.slice_tot = d_tot; a.sync = d_sync; a.count_vectors = d_cv; a.acc = d_acc;
     a.theta_tmp = d_tmp;
 
+    {
+        const char* e = getenv("RSEM_B200_GIBBS_FAST");
+        a.fast_rows = !(e && !strcmp(e, "0"));
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    const bool timing = getenv("RSEM_B200_TIMING") != nullptr;
+    if (timing) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, c->stream); }
     for (int base = 0; base < nc; base += chains_per_wave) {
         const int wave = std::min(nc - base, chains_per_wave);
         a.chain_base = base;
@@ -1347,6 +1448,7 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
         RB_TRYC(cudaLaunchCooperativeKernel(kernel, dim3(wave * (ctas + 1)), dim3(kPThreads), kargs, 0, c->stream));
         c->launches++;
     }
+    if (timing) cudaEventRecord(ev1, c->stream);
     std::vector<double> h_acc((size_t)nc * acc_per);
     std::vector<ChainSync> h_sync(nc);
     RB_TRYC(cudaMemcpyAsync(h_acc.data(), d_acc, h_acc.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1356,7 +1458,16 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
     cleanup();
 #undef RB_TRY
 #undef RB_TRYC
-    if (getenv("RSEM_B200_TIMING"))
+    if (timing) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        unsigned max_passes = 0;
+        for (int t = 0; t < nc; ++t) max_passes = std::max(max_passes, h_sync[t].passes);
+        fprintf(stderr, "gibbs kernels: %.2f ms on the device (walk variant %d, fast rows %d), most passes of a chain %u\n", ms, pf, a.fast_rows,
+                max_passes);
+    }
+    if (timing)
         fprintf(stderr, "gibbs chain 0 (%d worker CTAs, %d segments): %u passes; worker CTA 0 thread 0 cycles: wait for uniforms %llu, passes %llu, "
                 "barriers + bookkeeping %llu (incl. the passes), per-sample work %llu\n", ctas, g.n_segs, h_sync[0].passes, h_sync[0].prof[0],
                 h_sync[0].prof[1], h_sync[0].prof[2], h_sync[0].prof[3]);
