@@ -457,31 +457,103 @@ void load_dat(const std::string& path, int read_type, uint64_t expect_n1, HitSto
 }
 
 // ---- imd.ofg ---------------------------------------------------------------------------------------
+namespace {
+// Binary side-car of imd.ofg: the rows rsem-run-gibbs would parse from the text, in upload layout.  The values
+// are the doubles the TEXT denotes (15 significant digits, parsed back with strtod while the line is formatted), not the
+// unrounded conprb: the Gibbs draws must be the ones the reference makes from the text file.
+struct OfgHeader {
+    char magic[8];      // "RSEMOFG1"
+    uint64_t M, N0, rows, entries, ofg_bytes;
+};
+const char kOfgMagic[8] = {'R', 'S', 'E', 'M', 'O', 'F', 'G', '1'};
+
+uint64_t file_size_of(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return 0;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fclose(f);
+    return n < 0 ? 0 : (uint64_t)n;
+}
+}  // namespace
+
 void write_ofg(const std::string& path, int M, uint64_t N0, const HitStore& h, const std::vector<double>& conprb,
                const std::vector<double>& ncpv) {
     FILE* fo = fopen(path.c_str(), "w");
     if (!fo) die("Cannot open " + path + " for writing!");
     fprintf(fo, "%d %llu\n", M, (unsigned long long)N0);
+    const bool side = sidecar_enabled();
     const int T = std::max(1, std::min<int>(g_io_threads, (int)(h.H / 200000) + 1));
     std::vector<std::string> text(T);
+    struct Bin { std::vector<uint32_t> deg; std::vector<int32_t> sid; std::vector<double> val; };
+    std::vector<Bin> bin(T);
     parallel_ranges((size_t)h.N, T, [&](size_t b, size_t e, int t) {   // "%.15g" like ostream << setprecision(15)
         std::string& out = text[t];
+        Bin& bn = bin[t];
         out.reserve((size_t)((h.row_ptr[e] - h.row_ptr[b]) * 26 + (e - b) * 24));
+        if (side) { bn.sid.reserve((size_t)(h.row_ptr[e] - h.row_ptr[b]) + (e - b)); bn.val.reserve(bn.sid.capacity()); bn.deg.reserve(e - b); }
         char tmp[64];
+        auto emit = [&](int id, double v) {
+            const int n = snprintf(tmp, sizeof tmp, "%d %.15g ", id, v);
+            out.append(tmp, (size_t)n);
+            if (side) { bn.sid.push_back(id); bn.val.push_back(strtod(strchr(tmp, ' ') + 1, nullptr)); }
+        };
         for (size_t i = b; i < e; ++i) {
-            int tot = 0;
-            if (ncpv[i] >= kEps) { ++tot; out.append(tmp, (size_t)snprintf(tmp, sizeof tmp, "0 %.15g ", ncpv[i])); }
+            uint32_t tot = 0;
+            if (ncpv[i] >= kEps) { ++tot; emit(0, ncpv[i]); }
             for (uint64_t j = h.row_ptr[i]; j < h.row_ptr[i + 1]; ++j)
-                if (conprb[j] >= kEps) { ++tot; out.append(tmp, (size_t)snprintf(tmp, sizeof tmp, "%d %.15g ", abs(h.sid[j]), conprb[j])); }
-            if (tot > 0) out.push_back('\n');
+                if (conprb[j] >= kEps) { ++tot; emit(abs(h.sid[j]), conprb[j]); }
+            if (tot > 0) { out.push_back('\n'); if (side) bn.deg.push_back(tot); }
         }
     });
     for (const std::string& piece : text) fwrite(piece.data(), 1, piece.size(), fo);
-    fclose(fo);
+    if (fclose(fo) != 0) die("Cannot write " + path + " (disk full?)!");
+    if (!side) return;
+    OfgHeader hd;
+    memset(&hd, 0, sizeof hd);
+    memcpy(hd.magic, kOfgMagic, 8);
+    hd.M = (uint64_t)M;
+    hd.N0 = N0;
+    for (const Bin& bn : bin) { hd.rows += bn.deg.size(); hd.entries += bn.sid.size(); }
+    hd.ofg_bytes = file_size_of(path);
+    std::vector<uint64_t> row_ptr;
+    row_ptr.reserve((size_t)hd.rows + 1);
+    uint64_t at = 0;
+    row_ptr.push_back(0);
+    for (const Bin& bn : bin) for (uint32_t d : bn.deg) { at += d; row_ptr.push_back(at); }
+    FILE* fb = fopen((path + ".b200").c_str(), "wb");
+    if (!fb) die("Cannot open " + path + ".b200 for writing!");
+    bool ok = fwrite(&hd, sizeof hd, 1, fb) == 1 && fwrite(row_ptr.data(), 8, row_ptr.size(), fb) == row_ptr.size();
+    for (const Bin& bn : bin) ok = ok && (bn.sid.empty() || fwrite(bn.sid.data(), 4, bn.sid.size(), fb) == bn.sid.size());
+    for (const Bin& bn : bin) ok = ok && (bn.val.empty() || fwrite(bn.val.data(), 8, bn.val.size(), fb) == bn.val.size());
+    if (fclose(fb) != 0 || !ok) die("Cannot write " + path + ".b200 (disk full?)!");
+}
+
+// the side-car of `path`, if it is present and still describes the text file next to it
+static bool load_ofg_sidecar(const std::string& path, int M, uint64_t& N0, std::vector<uint64_t>& row_ptr, std::vector<int32_t>& sid,
+                             std::vector<double>& conprb) {
+    if (!sidecar_enabled()) return false;
+    FILE* fb = fopen((path + ".b200").c_str(), "rb");
+    if (!fb) return false;
+    OfgHeader hd;
+    bool ok = fread(&hd, sizeof hd, 1, fb) == 1 && !memcmp(hd.magic, kOfgMagic, 8) && hd.M == (uint64_t)M &&
+              hd.ofg_bytes == file_size_of(path) && hd.ofg_bytes > 0;
+    if (ok) {
+        row_ptr.resize((size_t)hd.rows + 1);
+        sid.resize((size_t)hd.entries);
+        conprb.resize((size_t)hd.entries);
+        ok = fread(row_ptr.data(), 8, row_ptr.size(), fb) == row_ptr.size() &&
+             (hd.entries == 0 || (fread(sid.data(), 4, sid.size(), fb) == sid.size() && fread(conprb.data(), 8, conprb.size(), fb) == conprb.size())) &&
+             row_ptr[0] == 0 && row_ptr[(size_t)hd.rows] == hd.entries;
+        N0 = hd.N0;
+    }
+    fclose(fb);
+    return ok;
 }
 
 void load_ofg(const std::string& path, int M, uint64_t& N0, std::vector<uint64_t>& row_ptr, std::vector<int32_t>& sid,
-              std::vector<double>& conprb) {
+              std::vector<double>& conprb, bool allow_sidecar) {
+    if (allow_sidecar && load_ofg_sidecar(path, M, N0, row_ptr, sid, conprb)) return;
     std::vector<char> buf = slurp(path, false);
     if (buf.empty()) die("Cannot open " + path + "!");
     if (buf.back() != '\n') buf.push_back('\n');

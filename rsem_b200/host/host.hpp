@@ -99,8 +99,10 @@ void finish_sidecar_reads(ReadStore& rs, const std::vector<ShortRead>& shorts, b
 // imd.ofg (EM.cpp:435-457 writer, Gibbs.cpp:101-137 reader); both split the rows over g_io_threads
 void write_ofg(const std::string& path, int M, uint64_t N0, const HitStore& h, const std::vector<double>& conprb,
                const std::vector<double>& ncpv);
+// load_ofg first tries the binary side-car `path`.b200 that write_ofg leaves next to the text (same rows, the doubles
+// the text denotes); it is used only while its recorded size of the text file still matches
 void load_ofg(const std::string& path, int M, uint64_t& N0, std::vector<uint64_t>& row_ptr, std::vector<int32_t>& sid,
-              std::vector<double>& conprb);
+              std::vector<double>& conprb, bool allow_sidecar = true);
 
 // ---- model -------------------------------------------------------------------------------------
 struct LenDistH {  // LenDist.h

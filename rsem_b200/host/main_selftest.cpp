@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -139,7 +140,19 @@ int main(int argc, char** argv) {
     std::vector<uint64_t> rp;
     std::vector<int32_t> sid;
     std::vector<double> con;
-    load_ofg(out + ".ofg", M, n0, rp, sid, con);
+    load_ofg(out + ".ofg", M, n0, rp, sid, con, false);   // the text
+    {   // and the binary side-car write_ofg left next to it: must be the very same arrays
+        uint64_t n0b = 0;
+        std::vector<uint64_t> rp2;
+        std::vector<int32_t> sid2;
+        std::vector<double> con2;
+        load_ofg(out + ".ofg", M, n0b, rp2, sid2, con2, true);
+        const bool same = n0b == n0 && rp2 == rp && sid2 == sid && con2.size() == con.size() &&
+                          (con.empty() || !memcmp(con2.data(), con.data(), con.size() * sizeof(double)));
+        FILE* sf = fopen((out + ".ofg.b200").c_str(), "rb");
+        printf("ofg_sidecar present %d identical %d\n", sf ? 1 : 0, same ? 1 : 0);
+        if (sf) fclose(sf);
+    }
     dump(out + ".ofg_row_ptr.u64", rp);
     dump(out + ".ofg_sid.i32", sid);
     dump(out + ".ofg_con.f64", con);

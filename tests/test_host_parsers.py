@@ -103,3 +103,27 @@ def test_parsers_match_an_independent_parse_for_every_thread_count(built, tmp_pa
     ref = open(outs[1] + ".ofg", "rb").read()
     for threads in (3, 8):
         assert open(outs[threads] + ".ofg", "rb").read() == ref
+
+
+def test_ofg_sidecar_is_the_text_parse(built, tmp_path):
+    """write_ofg leaves `<file>.ofg.b200` next to the text: the rows in upload layout with the doubles the TEXT
+    denotes (15 significant digits), so rsem-run-gibbs draws exactly what the reference draws from the text file.  The
+    selftest loads both and compares them bit for bit; RSEM_B200_SIDECAR=0 writes / reads no side-car."""
+    d = rf.gen_dataset(str(tmp_path / "d"), read_type=0, M=200, N1=20000, N0=300, avg_family=5, read_len=50, seed=9)
+    out = str(tmp_path / "o")
+    p = subprocess.run([EXE, f"{d}/s.temp/s", "0", "3", "25", out], stdout=subprocess.PIPE, text=True, check=True)
+    assert "ofg_sidecar present 1 identical 1" in p.stdout
+    hdr = np.fromfile(out + ".ofg.b200", dtype=np.uint64, count=6)
+    assert bytes(hdr[:1].tobytes()) == b"RSEMOFG1" and hdr[5] == os.path.getsize(out + ".ofg")
+    rows, entries = int(hdr[3]), int(hdr[4])
+    assert rows == sum(1 for _ in open(out + ".ofg")) - 1 and entries > rows
+    # the stored doubles are what Python parses from the text, not the unrounded inputs
+    vals = np.fromfile(out + ".ofg.b200", dtype=np.float64, offset=48 + 8 * (rows + 1) + 4 * entries)
+    text_vals = np.array([float(t) for line in list(open(out + ".ofg"))[1:] for t in line.split()[1::2]])
+    assert len(vals) == entries and np.array_equal(vals, text_vals)
+    assert not np.array_equal(vals, np.fromfile(out + ".in_con.f64")[: len(vals)])
+    out2 = str(tmp_path / "o2")
+    p = subprocess.run([EXE, f"{d}/s.temp/s", "0", "3", "25", out2], stdout=subprocess.PIPE, text=True, check=True,
+                       env=dict(os.environ, RSEM_B200_SIDECAR="0"))
+    assert "ofg_sidecar present 0 identical 1" in p.stdout and not os.path.exists(out2 + ".ofg.b200")
+    assert open(out2 + ".ofg", "rb").read() == open(out + ".ofg", "rb").read()
