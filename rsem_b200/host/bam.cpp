@@ -14,6 +14,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,14 +61,135 @@ int aux_type_size(char x) {  // sam_utils.h:24-30
 
 }  // namespace
 
-// ---- raw byte source: plain file or gzip / BGZF (zlib's gz* layer reads concatenated members transparently) ---------
+// ---- raw byte source ----------------------------------------------------------------------------------------------------
+// plain text / gzip: zlib's gz* layer.  BGZF (every BAM, bgzip'ed SAM): the file is a sequence of independent deflate blocks
+// of <= 64 KB, so a producer thread reads the compressed blocks in order and inflates a batch of them on g_io_threads
+// worker threads straight into the batch's final buffer (offsets = prefix sums of the blocks' ISIZE fields) while the
+// consumer parses the previous batch.  The reference reads its input with htslib's single-threaded BGZF reader.
 struct AlnReader::Source {
     gzFile gz = nullptr;
     std::vector<uint8_t> buf;
     size_t at = 0, end = 0;
     bool eof = false;
+
+    // BGZF mode
+    FILE* fp = nullptr;
+    std::thread producer;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::vector<uint8_t>> ready;   // decoded batches, in file order
+    bool done = false, stop = false;
+
+    static bool looks_like_bgzf(const uint8_t* h, size_t n) {
+        return n >= 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0;
+    }
+    void start_bgzf(const std::string& path) {
+        fp = fopen(path.c_str(), "rb");
+        if (!fp) die("Cannot open " + path + "! It may not exist.");
+        producer = std::thread([this]() { produce(); });
+    }
+    // one batch: up to kBlocks compressed blocks read in order, inflated in parallel
+    void produce() {
+        constexpr size_t kBlocks = 512;
+        struct Blk { size_t c_off, c_len, u_off, u_len; };
+        std::vector<uint8_t> comp;
+        std::vector<Blk> blks;
+        bool file_end = false;
+        while (!file_end) {
+            comp.clear();
+            blks.clear();
+            size_t u_total = 0;
+            while (blks.size() < kBlocks) {
+                uint8_t h[12];
+                const size_t got = fread(h, 1, 12, fp);
+                if (got == 0) { file_end = true; break; }
+                if (got != 12 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) die("Corrupt BGZF block header in the alignment file!");
+                const size_t xlen = rd_u16(h + 10);
+                uint8_t extra[256];
+                if (xlen > sizeof extra || fread(extra, 1, xlen, fp) != xlen) die("Corrupt BGZF block header in the alignment file!");
+                size_t bsize = 0;
+                for (size_t k = 0; k + 4 <= xlen;) {
+                    const size_t slen = rd_u16(extra + k + 2);
+                    if (extra[k] == 'B' && extra[k + 1] == 'C' && slen == 2) bsize = (size_t)rd_u16(extra + k + 4) + 1;
+                    k += 4 + slen;
+                }
+                if (bsize < 12 + xlen + 8) die("Corrupt BGZF block (no BC field) in the alignment file!");
+                const size_t rest = bsize - 12 - xlen;   // deflate data + CRC32 + ISIZE
+                const size_t c_off = comp.size();
+                comp.resize(c_off + rest);
+                if (fread(comp.data() + c_off, 1, rest, fp) != rest) die("Truncated BGZF block in the alignment file!");
+                const size_t u_len = rd_u32(comp.data() + c_off + rest - 4);
+                if (u_len > 65536) die("Corrupt BGZF block (ISIZE) in the alignment file!");
+                blks.push_back(Blk{c_off, rest - 8, u_total, u_len});
+                u_total += u_len;
+            }
+            if (!blks.empty()) {
+                std::vector<uint8_t> out(u_total);
+                std::atomic<size_t> next(0);
+                std::atomic<int> bad(0);
+                auto work = [&]() {
+                    z_stream zs;
+                    for (;;) {
+                        const size_t i = next.fetch_add(1);
+                        if (i >= blks.size()) break;
+                        const Blk& k = blks[i];
+                        if (k.u_len == 0) continue;
+                        memset(&zs, 0, sizeof zs);
+                        if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; continue; }
+                        zs.next_in = comp.data() + k.c_off;
+                        zs.avail_in = (uInt)k.c_len;
+                        zs.next_out = out.data() + k.u_off;
+                        zs.avail_out = (uInt)k.u_len;
+                        const int rc = inflate(&zs, Z_FINISH);
+                        if (rc != Z_STREAM_END || zs.total_out != k.u_len) bad = 1;
+                        inflateEnd(&zs);
+                    }
+                };
+                const int nt = (int)std::min<size_t>((size_t)std::max(1, g_io_threads), blks.size());
+                if (nt <= 1) work();
+                else {
+                    std::vector<std::thread> pool;
+                    for (int t = 0; t < nt; ++t) pool.emplace_back(work);
+                    for (auto& t : pool) t.join();
+                }
+                if (bad) die("Error while reading the alignment file (corrupt gzip / BGZF stream)!");
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&]() { return ready.size() < 3 || stop; });
+                if (stop) return;
+                ready.push_back(std::move(out));
+                cv.notify_all();
+            }
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        done = true;
+        cv.notify_all();
+    }
+    ~Source() {
+        if (producer.joinable()) {
+            { std::lock_guard<std::mutex> lk(mu); stop = true; }
+            cv.notify_all();
+            producer.join();
+        }
+        if (fp) fclose(fp);
+        if (gz) gzclose(gz);
+    }
+
     bool fill() {
         if (eof) return false;
+        if (fp) {   // BGZF: callers come here only with an empty buffer
+            std::unique_lock<std::mutex> lk(mu);
+            for (;;) {
+                cv.wait(lk, [&]() { return !ready.empty() || done; });
+                if (ready.empty()) { eof = true; return false; }
+                buf = std::move(ready.front());
+                ready.pop_front();
+                cv.notify_all();
+                if (!buf.empty()) break;
+            }
+            at = 0;
+            end = buf.size();
+            return true;
+        }
         if (at < end) memmove(buf.data(), buf.data() + at, end - at);
         end -= at;
         at = 0;
@@ -90,20 +214,43 @@ struct AlnReader::Source {
         }
         return true;
     }
-    bool line(std::string& out) {  // one text line without the terminator
-        out.clear();
-        for (;;) {
-            if (at == end && !fill()) return !out.empty();
-            const uint8_t* p = static_cast<const uint8_t*>(memchr(buf.data() + at, '\n', end - at));
-            if (p) {
-                out.append(reinterpret_cast<const char*>(buf.data() + at), (size_t)(p - (buf.data() + at)));
-                at = (size_t)(p - buf.data()) + 1;
-                if (!out.empty() && out.back() == '\r') out.pop_back();
-                return true;
-            }
-            out.append(reinterpret_cast<const char*>(buf.data() + at), end - at);
+    // one text line without the terminator: [*p, *p + *n) points into the buffer when the line lies inside it (the common
+    // case), otherwise into `spill`
+    bool line_view(const char*& p, size_t& n, std::string& spill) {
+        if (at == end && !fill()) return false;
+        const uint8_t* nl = static_cast<const uint8_t*>(memchr(buf.data() + at, '\n', end - at));
+        if (nl) {
+            p = reinterpret_cast<const char*>(buf.data() + at);
+            n = (size_t)(nl - (buf.data() + at));
+            at += n + 1;
+        } else {   // the line crosses a buffer boundary
+            spill.assign(reinterpret_cast<const char*>(buf.data() + at), end - at);
             at = end;
+            for (;;) {
+                if (at == end && !fill()) break;
+                const uint8_t* q = static_cast<const uint8_t*>(memchr(buf.data() + at, '\n', end - at));
+                if (q) {
+                    spill.append(reinterpret_cast<const char*>(buf.data() + at), (size_t)(q - (buf.data() + at)));
+                    at = (size_t)(q - buf.data()) + 1;
+                    break;
+                }
+                spill.append(reinterpret_cast<const char*>(buf.data() + at), end - at);
+                at = end;
+            }
+            if (spill.empty() && eof) return false;
+            p = spill.data();
+            n = spill.size();
         }
+        if (n && p[n - 1] == '\r') --n;
+        return true;
+    }
+    bool line(std::string& out) {
+        const char* p;
+        size_t n;
+        std::string spill;
+        if (!line_view(p, n, spill)) { out.clear(); return false; }
+        out.assign(p, n);
+        return true;
     }
 };
 
@@ -114,10 +261,19 @@ AlnReader::AlnReader(const std::string& path) : src_(new Source) {
     const size_t got = fread(magic, 1, 4, probe);
     fclose(probe);
     if (got >= 4 && !memcmp(magic, "CRAM", 4)) die("rsem-run-em (B200): CRAM input for -b is not supported; convert it to BAM (convert-sam-for-rsem).");
-    src_->gz = gzopen(path.c_str(), "rb");
-    if (!src_->gz) die("Cannot open " + path + "! It may not exist.");
-    gzbuffer(src_->gz, 1 << 20);
-    src_->buf.resize(4 << 20);
+    uint8_t head[18] = {0};
+    {
+        FILE* p2 = fopen(path.c_str(), "rb");
+        const size_t hn = p2 ? fread(head, 1, 18, p2) : 0;
+        if (p2) fclose(p2);
+        if (Source::looks_like_bgzf(head, hn)) src_->start_bgzf(path);
+    }
+    if (!src_->fp) {
+        src_->gz = gzopen(path.c_str(), "rb");
+        if (!src_->gz) die("Cannot open " + path + "! It may not exist.");
+        gzbuffer(src_->gz, 1 << 20);
+        src_->buf.resize(4 << 20);
+    }
     // BAM = gzip stream whose payload starts with "BAM\1"; anything else is SAM text
     uint8_t m4[4];
     src_->fill();
@@ -169,10 +325,7 @@ AlnReader::AlnReader(const std::string& path) : src_(new Source) {
     for (size_t i = 0; i < ref_names_.size(); ++i) ref_index_[ref_names_[i]] = (int)i;
 }
 
-AlnReader::~AlnReader() {
-    if (src_->gz) gzclose(src_->gz);
-    delete src_;
-}
+AlnReader::~AlnReader() { delete src_; }
 
 bool AlnReader::next(BamRecord& rec) {
     if (is_bam_) {
@@ -184,74 +337,112 @@ bool AlnReader::next(BamRecord& rec) {
         if (!src_->read(rec.data.data(), block)) die("Truncated BAM file!");
         return true;
     }
-    std::string ln;
-    if (have_pending_) { ln.swap(pending_); have_pending_ = false; }
-    else {
-        do {
-            if (!src_->line(ln)) return false;
-        } while (ln.empty());
+    if (have_pending_) {
+        have_pending_ = false;
+        parse_sam_line(pending_.data(), pending_.size(), rec);
+        return true;
     }
-    parse_sam_line(ln, rec);
+    const char* p;
+    size_t n;
+    do {
+        if (!src_->line_view(p, n, spill_)) return false;
+    } while (n == 0);
+    parse_sam_line(p, n, rec);
     return true;
 }
 
-// SAM text -> BAM record (SAM spec section 4.2; field encodings as htslib's sam_parse1 chooses them)
-void AlnReader::parse_sam_line(const std::string& ln, BamRecord& rec) const {
-    std::vector<std::pair<size_t, size_t>> f;  // [begin, end) of every tab-separated field
-    for (size_t fr = 0; fr <= ln.size();) {
-        size_t to = ln.find('\t', fr);
-        if (to == std::string::npos) to = ln.size();
-        f.emplace_back(fr, to);
-        fr = to + 1;
+// SAM text -> BAM record (SAM spec section 4.2; field encodings as htslib's sam_parse1 chooses them).  No allocation per
+// line: fields are (pointer, length) views into the reader's buffer, the record's byte vector is reused by the caller.
+void AlnReader::parse_sam_line(const char* ln, size_t len, BamRecord& rec) const {
+    struct Fld { const char* p; size_t n; };
+    Fld f[11];
+    const char* end = ln + len;
+    const char* q = ln;
+    int nf = 0;
+    while (nf < 11) {
+        const char* t = static_cast<const char*>(memchr(q, '\t', (size_t)(end - q)));
+        f[nf].p = q;
+        f[nf].n = (size_t)((t ? t : end) - q);
+        ++nf;
+        if (!t) { q = end; break; }
+        q = t + 1;
     }
-    if (f.size() < 11) die("Malformed SAM line (fewer than 11 fields): " + ln.substr(0, 80));
-    auto S = [&](int i) { return ln.substr(f[i].first, f[i].second - f[i].first); };
-    const std::string qname = S(0), rname = S(2), cigar = S(5), rnext = S(6), seq = S(9), qual = S(10);
-    const int flag = atoi(S(1).c_str());
-    const int64_t pos = atoll(S(3).c_str()) - 1, pnext = atoll(S(7).c_str()) - 1, tlen = atoll(S(8).c_str());
-    const int mapq = atoi(S(4).c_str());
-    auto ref_id = [&](const std::string& n) -> int {
-        if (n == "*") return -1;
-        auto it = ref_index_.find(n);
-        if (it == ref_index_.end()) die("SAM line refers to a reference sequence that is not in the header: " + n);
+    if (nf < 11) die("Malformed SAM line (fewer than 11 fields): " + std::string(ln, std::min<size_t>(len, 80)));
+    const char* opt = (f[10].p + f[10].n < end) ? f[10].p + f[10].n + 1 : end;   // first optional field
+    auto to_i64 = [](const Fld& x) {   // atoll on a view
+        const char* s = x.p;
+        const char* e = x.p + x.n;
+        bool neg = false;
+        if (s < e && (*s == '-' || *s == '+')) { neg = *s == '-'; ++s; }
+        long long v = 0;
+        while (s < e && *s >= '0' && *s <= '9') v = v * 10 + (*s++ - '0');
+        return neg ? -v : v;
+    };
+    auto is = [](const Fld& x, char c) { return x.n == 1 && x.p[0] == c; };
+    const Fld &qname = f[0], &rname = f[2], &cigar = f[5], &rnext = f[6], &seq = f[9], &qual = f[10];
+    const int flag = (int)to_i64(f[1]);
+    const int64_t pos = to_i64(f[3]) - 1, pnext = to_i64(f[7]) - 1, tlen = to_i64(f[8]);
+    const int mapq = (int)to_i64(f[4]);
+    auto ref_id = [&](const Fld& x) -> int {
+        if (is(x, '*')) return -1;
+        if (last_ref_ >= 0 && ref_names_[(size_t)last_ref_].size() == x.n && !memcmp(ref_names_[(size_t)last_ref_].data(), x.p, x.n))
+            return last_ref_;
+        auto it = ref_index_.find(std::string(x.p, x.n));
+        if (it == ref_index_.end()) die("SAM line refers to a reference sequence that is not in the header: " + std::string(x.p, x.n));
+        last_ref_ = it->second;
         return it->second;
     };
     const int tid = ref_id(rname);
-    const int mtid = rnext == "=" ? tid : ref_id(rnext);
+    const int mtid = is(rnext, '=') ? tid : ref_id(rnext);
     // CIGAR
-    std::vector<uint32_t> cig;
+    uint32_t cig[64];
+    std::vector<uint32_t> cig_big;
+    size_t n_cig = 0;
     int64_t ref_len = 0;
-    if (cigar != "*") {
-        static const char* OPS = "MIDNSHP=X";
-        const char* p = cigar.c_str();
-        while (*p) {
-            char* q;
-            const unsigned long n = strtoul(p, &q, 10);
-            const char* o = strchr(OPS, *q);
-            if (q == p || !*q || !o) die("Malformed CIGAR string: " + cigar);
-            const uint32_t op = (uint32_t)(o - OPS);
-            cig.push_back((uint32_t)(n << 4) | op);
+    if (!is(cigar, '*')) {
+        const char* p = cigar.p;
+        const char* e = cigar.p + cigar.n;
+        while (p < e) {
+            unsigned long n = 0;
+            const char* d0 = p;
+            while (p < e && *p >= '0' && *p <= '9') n = n * 10 + (unsigned long)(*p++ - '0');
+            uint32_t op;
+            switch (p < e ? *p : 0) {
+                case 'M': op = 0; break; case 'I': op = 1; break; case 'D': op = 2; break; case 'N': op = 3; break;
+                case 'S': op = 4; break; case 'H': op = 5; break; case 'P': op = 6; break; case '=': op = 7; break;
+                case 'X': op = 8; break;
+                default: op = 99;
+            }
+            if (p == d0 || op == 99) die("Malformed CIGAR string: " + std::string(cigar.p, cigar.n));
+            const uint32_t w = (uint32_t)(n << 4) | op;
+            if (n_cig < 64) cig[n_cig] = w;
+            else { if (n_cig == 64) cig_big.assign(cig, cig + 64); cig_big.push_back(w); }
+            ++n_cig;
             if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_len += (int64_t)n;
-            p = q + 1;
+            ++p;
         }
     }
-    const int l_seq = seq == "*" ? 0 : (int)seq.size();
+    const uint32_t* cg = n_cig > 64 ? cig_big.data() : cig;
+    const int l_seq = is(seq, '*') ? 0 : (int)seq.n;
     std::vector<uint8_t>& d = rec.data;
-    d.clear();
-    d.reserve(32 + qname.size() + 1 + cig.size() * 4 + (l_seq + 1) / 2 + l_seq + 64);
-    const int64_t end = (flag & 4) || cig.empty() || ref_len == 0 ? pos + 1 : pos + ref_len;
-    put<int32_t>(d, tid);
-    put<int32_t>(d, (int32_t)pos);
+    const size_t fixed = 32 + qname.n + 1 + n_cig * 4 + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+    d.resize(fixed);
+    uint8_t* w = d.data();
+    const int64_t endp = (flag & 4) || n_cig == 0 || ref_len == 0 ? pos + 1 : pos + ref_len;
+    wr_u32(w, (uint32_t)tid);
+    wr_u32(w + 4, (uint32_t)(int32_t)pos);
     // an unplaced record (pos = -1) gets bin 4680 = reg2bin(-1, 0), as htslib computes it
-    put<uint32_t>(d, ((uint32_t)reg2bin(pos, end) << 16) | ((uint32_t)(mapq & 255) << 8) | (uint32_t)(qname.size() + 1));
-    put<uint32_t>(d, ((uint32_t)flag << 16) | (uint32_t)cig.size());
-    put<int32_t>(d, l_seq);
-    put<int32_t>(d, mtid);
-    put<int32_t>(d, (int32_t)pnext);
-    put<int32_t>(d, (int32_t)tlen);
-    d.insert(d.end(), qname.begin(), qname.end());
-    d.push_back(0);
-    for (uint32_t c : cig) put<uint32_t>(d, c);
+    wr_u32(w + 8, ((uint32_t)reg2bin(pos, endp) << 16) | ((uint32_t)(mapq & 255) << 8) | (uint32_t)(qname.n + 1));
+    wr_u32(w + 12, ((uint32_t)flag << 16) | (uint32_t)n_cig);
+    wr_u32(w + 16, (uint32_t)l_seq);
+    wr_u32(w + 20, (uint32_t)mtid);
+    wr_u32(w + 24, (uint32_t)(int32_t)pnext);
+    wr_u32(w + 28, (uint32_t)(int32_t)tlen);
+    w += 32;
+    memcpy(w, qname.p, qname.n);
+    w += qname.n;
+    *w++ = 0;
+    for (size_t i = 0; i < n_cig; ++i) { wr_u32(w, cg[i]); w += 4; }
     static uint8_t nt16[256];
     static bool nt_init = false;
     if (!nt_init) {
@@ -261,22 +452,23 @@ void AlnReader::parse_sam_line(const std::string& ln, BamRecord& rec) const {
         nt_init = true;
     }
     for (int i = 0; i < l_seq; i += 2) {
-        const uint8_t hi = nt16[(uint8_t)seq[i]], lo = i + 1 < l_seq ? nt16[(uint8_t)seq[i + 1]] : 0;
-        d.push_back((uint8_t)(hi << 4 | lo));
+        const uint8_t hi = nt16[(uint8_t)seq.p[i]], lo = i + 1 < l_seq ? nt16[(uint8_t)seq.p[i + 1]] : 0;
+        *w++ = (uint8_t)(hi << 4 | lo);
     }
-    if (qual == "*") d.insert(d.end(), (size_t)l_seq, 0xff);
+    if (is(qual, '*')) { memset(w, 0xff, (size_t)l_seq); w += l_seq; }
     else {
-        if ((int)qual.size() != l_seq) die("SAM line with SEQ and QUAL of different lengths: " + qname);
-        for (int i = 0; i < l_seq; ++i) d.push_back((uint8_t)(qual[i] - 33));
+        if ((int)qual.n != l_seq) die("SAM line with SEQ and QUAL of different lengths: " + std::string(qname.p, qname.n));
+        for (int i = 0; i < l_seq; ++i) *w++ = (uint8_t)(qual.p[i] - 33);
     }
     // optional fields
-    for (size_t k = 11; k < f.size(); ++k) {
-        const size_t a = f[k].first, b = f[k].second;
-        if (b - a < 5 || ln[a + 2] != ':' || ln[a + 4] != ':') die("Malformed optional SAM field in the line of " + qname);
-        const char type = ln[a + 3];
-        const std::string val = ln.substr(a + 5, b - a - 5);
-        d.push_back((uint8_t)ln[a]);
-        d.push_back((uint8_t)ln[a + 1]);
+    for (const char* a = opt; a < end;) {
+        const char* t = static_cast<const char*>(memchr(a, '\t', (size_t)(end - a)));
+        const char* b = t ? t : end;
+        if (b - a < 5 || a[2] != ':' || a[4] != ':') die("Malformed optional SAM field in the line of " + std::string(qname.p, qname.n));
+        const char type = a[3];
+        const std::string val(a + 5, (size_t)(b - a - 5));
+        d.push_back((uint8_t)a[0]);
+        d.push_back((uint8_t)a[1]);
         if (type == 'A') { d.push_back('A'); d.push_back((uint8_t)(val.empty() ? ' ' : val[0])); }
         else if (type == 'i') {
             const long long x = atoll(val.c_str());
@@ -296,7 +488,7 @@ void AlnReader::parse_sam_line(const std::string& ln, BamRecord& rec) const {
             d.insert(d.end(), val.begin(), val.end());
             d.push_back(0);
         } else if (type == 'B') {
-            if (val.empty()) die("Malformed B-type optional field in the line of " + qname);
+            if (val.empty()) die("Malformed B-type optional field in the line of " + std::string(qname.p, qname.n));
             const char sub = val[0];
             std::vector<std::string> items;
             for (size_t fr = 1; fr < val.size();) {
@@ -318,10 +510,11 @@ void AlnReader::parse_sam_line(const std::string& ln, BamRecord& rec) const {
                     case 'i': put<int32_t>(d, (int32_t)atoll(it.c_str())); break;
                     case 'I': put<uint32_t>(d, (uint32_t)atoll(it.c_str())); break;
                     case 'f': put<float>(d, (float)atof(it.c_str())); break;
-                    default: die("Unknown B-array subtype in the line of " + qname);
+                    default: die("Unknown B-array subtype in the line of " + std::string(qname.p, qname.n));
                 }
             }
-        } else die("Unknown optional field type in the line of " + qname);
+        } else die("Unknown optional field type in the line of " + std::string(qname.p, qname.n));
+        a = t ? t + 1 : end;
     }
 }
 

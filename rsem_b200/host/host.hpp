@@ -222,7 +222,9 @@ private:
     std::vector<std::string> ref_names_;
     std::vector<uint32_t> ref_lens_;
     std::map<std::string, int> ref_index_;
-    void parse_sam_line(const std::string& ln, BamRecord& rec) const;
+    mutable int last_ref_ = -1;   // RNAME of the previous line (alignments of a read mostly share it or repeat it)
+    std::string spill_;           // a line that crosses a buffer boundary
+    void parse_sam_line(const char* ln, size_t len, BamRecord& rec) const;
 };
 
 std::string rsem_bam_header_text(const std::string& in_text);  // SamHeader(text) + insertPG("RSEM")

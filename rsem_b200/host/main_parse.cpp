@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <thread>
 
 #include "host.hpp"
 
@@ -61,30 +62,39 @@ struct Hit { int32_t sid, pos, insertL; };
 
 const char* kWhitespace = " \t\n\r\f\v";
 
+// decimal text of v at p, returns the new end (the .dat body is ~10 such numbers per alignment)
+inline char* put_int(char* p, long long v) {
+    if (v < 0) { *p++ = '-'; v = -v; }
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+// length of the canonical read name: the first whitespace-delimited word of QNAME (sam_utils.h:58-65)
+inline size_t canonical_len(const char* raw) { return strcspn(raw, kWhitespace); }
+
 // sam_utils.h:58-65: only the first whitespace-delimited word of QNAME
 std::string canonical_name(const BamRecord& b) {
     const char* raw = b.qname();
-    const char* ws = strpbrk(raw, kWhitespace);
-    return ws ? std::string(raw, (size_t)(ws - raw)) : std::string(raw);
+    return std::string(raw, canonical_len(raw));
 }
 
 // sam_utils.h:78-117: the read as it was sequenced (reverse-complemented back for reverse-strand alignments)
 void read_seq(const BamRecord& b, std::string& out) {
+    static const char fwd[17] = "\0AC\0G\0\0\0T\0\0\0\0\0\0N", rvs[17] = "\0TG\0C\0\0\0A\0\0\0\0\0\0N";
     const int n = b.l_seq();
     out.resize((size_t)n);
     const bool rev = b.reverse();
+    const char* lut = rev ? rvs : fwd;
+    char bad = 1;
     for (int i = 0; i < n; ++i) {
-        char c = 0;
-        switch (b.base4(rev ? n - 1 - i : i)) {
-            case 1: c = rev ? 'T' : 'A'; break;
-            case 2: c = rev ? 'G' : 'C'; break;
-            case 4: c = rev ? 'C' : 'G'; break;
-            case 8: c = rev ? 'A' : 'T'; break;
-            case 15: c = 'N'; break;
-            default: die("Read " + canonical_name(b) + " contains a base other than A, C, G, T and N (reference: assert(false) in bam_get_read_seq)!");
-        }
+        const char c = lut[b.base4(rev ? n - 1 - i : i)];
+        bad &= c != 0;
         out[(size_t)i] = c;
     }
+    if (!bad) die("Read " + canonical_name(b) + " contains a base other than A, C, G, T and N (reference: assert(false) in bam_get_read_seq)!");
 }
 
 // sam_utils.h:119-139
@@ -127,22 +137,24 @@ struct Parser {
     int next(Read& read, Hit& hit) {
         if (!paired) {
             if (!in->next(b)) return -1;
-            const std::string name = canonical_name(b);
-            if (b.paired()) die("Read " + name + ": Find a paired end read in the file!");
+            const char* raw = b.qname();
+            const size_t nlen = canonical_len(raw);
+            if (b.paired()) die("Read " + std::string(raw, nlen) + ": Find a paired end read in the file!");
             const int type = b.mapped() ? 1 : tag_type(b);
             int val;
-            if (type != 1 || read.name != name) {
+            if (type != 1 || read.name.size() != nlen || memcmp(read.name.data(), raw, nlen) != 0) {
                 val = type;
+                const std::string name(raw, nlen);
                 read.name = name;
                 read.mate[0].name = name;
                 read_seq(b, read.mate[0].seq);
                 if (hasq) read_qual(b, read.mate[0].qual);
             } else {
-                if ((int)read.mate[0].seq.size() != b.l_seq()) die("Read " + name + " has alignments with inconsistent read lengths!");
+                if ((int)read.mate[0].seq.size() != b.l_seq()) die("Read " + std::string(raw, nlen) + " has alignments with inconsistent read lengths!");
                 val = 5;
             }
             if (type == 1) {
-                if (!cigar_ok(b)) die("Read " + name + ": RSEM currently does not support gapped alignments, sorry!\n");
+                if (!cigar_ok(b)) die("Read " + std::string(raw, nlen) + ": RSEM currently does not support gapped alignments, sorry!\n");
                 const int sid = internal_sid(b);
                 if (b.reverse()) hit = Hit{-sid, (int32_t)in->ref_lens()[(size_t)b.tid()] - b.pos() - b.l_seq(), 0};
                 else hit = Hit{sid, b.pos(), 0};
@@ -151,35 +163,40 @@ struct Parser {
         }
         if (!in->next(b) || !in->next(b2)) return -1;
         if (!b.read1()) b.data.swap(b2.data);
-        const std::string name = canonical_name(b);
+        const char* raw = b.qname();
+        const size_t nlen = canonical_len(raw);
+        const char* raw2 = b2.qname();
+        const size_t nlen2 = canonical_len(raw2);
+        auto name_of = [&]() { return std::string(raw, nlen); };
         if (!(b.paired() && b2.paired()))
-            die("Read " + name + ": One of the mate is not paired-end! (RSEM assumes the two mates of a paired-end read should be adjacent)");
+            die("Read " + name_of() + ": One of the mate is not paired-end! (RSEM assumes the two mates of a paired-end read should be adjacent)");
         if (!(b.read1() && b2.read2()))
-            die("Read " + name + ": The adjacent two lines do not represent the two mates of a paired-end read! (RSEM assumes the two mates of a paired-end read should be adjacent)");
-        if (b.mapped() != b2.mapped()) die("Read " + name + ": RSEM currently does not support partial alignments!");
-        const std::string name2 = canonical_name(b2);
-        if (name != name2 && ++n_warns <= 50)   // MAX_WARNS, utils.h
-            fprintf(stderr, "Warning: Detected a read pair whose two mates have different names--%s and %s!\n", name.c_str(), name2.c_str());
+            die("Read " + name_of() + ": The adjacent two lines do not represent the two mates of a paired-end read! (RSEM assumes the two mates of a paired-end read should be adjacent)");
+        if (b.mapped() != b2.mapped()) die("Read " + name_of() + ": RSEM currently does not support partial alignments!");
+        if ((nlen != nlen2 || memcmp(raw, raw2, nlen) != 0) && ++n_warns <= 50)   // MAX_WARNS, utils.h
+            fprintf(stderr, "Warning: Detected a read pair whose two mates have different names--%s and %s!\n", name_of().c_str(),
+                    std::string(raw2, nlen2).c_str());
         int type;
         if (b.mapped() && b2.mapped()) type = 1;
         else type = (tag_type(b) == 2 || tag_type(b2) == 2) ? 2 : 0;
         int val;
-        if (type != 1 || read.name != name) {
+        if (type != 1 || read.name.size() != nlen || memcmp(read.name.data(), raw, nlen) != 0) {
             val = type;
+            const std::string name = name_of();
             read.name = name;
             read.mate[0].name = name;
-            read.mate[1].name = name2;
+            read.mate[1].name.assign(raw2, nlen2);
             read_seq(b, read.mate[0].seq);
             read_seq(b2, read.mate[1].seq);
             if (hasq) { read_qual(b, read.mate[0].qual); read_qual(b2, read.mate[1].qual); }
         } else {
             if (!((int)read.mate[0].seq.size() == b.l_seq() && (int)read.mate[1].seq.size() == b2.l_seq()))
-                die("Paired-end read " + name + " has alignments with inconsistent mate lengths!");
+                die("Paired-end read " + name_of() + " has alignments with inconsistent mate lengths!");
             val = 5;
         }
         if (type == 1) {
-            if (!(cigar_ok(b) && cigar_ok(b2))) die("Read " + name + ": RSEM currently does not support gapped alignments, sorry!");
-            if (b.tid() != b2.tid()) die("Read " + name + ": The two mates do not align to a same transcript! RSEM does not support discordant alignments.");
+            if (!(cigar_ok(b) && cigar_ok(b2))) die("Read " + name_of() + ": RSEM currently does not support gapped alignments, sorry!");
+            if (b.tid() != b2.tid()) die("Read " + name_of() + ": The two mates do not align to a same transcript! RSEM does not support discordant alignments.");
             const int sid = internal_sid(b);
             if (b.reverse())
                 hit = Hit{-sid, (int32_t)in->ref_lens()[(size_t)b.tid()] - b.pos() - b.l_seq(), b.pos() + b.l_seq() - b2.pos()};
@@ -197,8 +214,15 @@ void append_read(ReadStore& rs, std::vector<ShortRead>& shorts, const Read& r, i
     for (int m = 0; m < n_mates; ++m) {
         const Mate& mt = r.mate[m];
         if (rs.off[m].empty()) rs.off[m].push_back(0);
-        for (char c : mt.seq) rs.base[m].push_back((uint8_t)g_base_code[(unsigned char)c]);
-        if (hasq) for (char c : mt.qual) rs.qual[m].push_back((uint8_t)((unsigned char)c - 33));
+        const size_t n = mt.seq.size(), at = rs.base[m].size();
+        rs.base[m].resize(at + n);
+        uint8_t* bd = rs.base[m].data() + at;
+        for (size_t k = 0; k < n; ++k) bd[k] = (uint8_t)g_base_code[(unsigned char)mt.seq[k]];
+        if (hasq) {
+            rs.qual[m].resize(at + n);
+            uint8_t* qd = rs.qual[m].data() + at;
+            for (size_t k = 0; k < n; ++k) qd[k] = (uint8_t)((unsigned char)mt.qual[k] - 33);
+        }
         rs.off[m].push_back(rs.off[m].back() + mt.seq.size());
         is_short = is_short || (int)mt.seq.size() < kSidecarShortLen;
     }
@@ -223,6 +247,10 @@ int main(int argc, char* argv[]) {
         if (!strcmp(argv[i], "-q")) g_verbose = false;
     }
     if (read_type < 0 || read_type > 3) die("Unknown Read Type!");
+    {   // the reference has no -p here; host threads inflate the BGZF blocks of the input (RSEM_B200_IO_THREADS, default <= 8)
+        const char* e = getenv("RSEM_B200_IO_THREADS");
+        g_io_threads = e ? std::max(1, atoi(e)) : (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    }
     if (!ps.rt_tag.empty() && ps.rt_tag.size() != 2) die("-tag expects a two-character SAM tag!");
     ps.read_type = read_type;
     ps.hasq = read_type & 1;
@@ -315,10 +343,13 @@ int main(int argc, char* argv[]) {
         std::sort(gids.begin(), gids.end());
         if (std::unique(gids.begin(), gids.end()) - gids.begin() > 1) ++nMulti;
         if (k > 1) ++nIsoMulti;
-        dat.put(tmp, (size_t)snprintf(tmp, sizeof tmp, "%zu", k));
+        dat.put(tmp, (size_t)(put_int(tmp, (long long)k) - tmp));
         for (const Hit& h : hits) {
-            if (ps.paired) dat.put(tmp, (size_t)snprintf(tmp, sizeof tmp, " %d %d %d", h.sid, h.pos, h.insertL));
-            else dat.put(tmp, (size_t)snprintf(tmp, sizeof tmp, " %d %d", h.sid, h.pos));
+            char* e = tmp;
+            *e++ = ' '; e = put_int(e, h.sid);
+            *e++ = ' '; e = put_int(e, h.pos);
+            if (ps.paired) { *e++ = ' '; e = put_int(e, h.insertL); }
+            dat.put(tmp, (size_t)(e - tmp));
             sc.hits.sid.push_back(h.sid);
             sc.hits.pos.push_back(h.pos);
             if (ps.paired) sc.hits.insertL.push_back(h.insertL);
