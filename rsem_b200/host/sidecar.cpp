@@ -3,14 +3,14 @@
 // EM.cpp:127-132) and its per-round re-parse of the read files (EM.cpp:195-202).  The text files remain the contract
 // (they are always written, byte-identical to the reference's); the side-car is the same content in upload layout:
 //
-//   header   magic "RSEMB200", version, read_type, N[3], H, byte sizes of imd.dat and of the six read files, the
-//            short-read length threshold
+//   header   magic "RSEMB200", version, read_type, N[3], H, byte sizes of imd.dat and of the six read files, a hash of the
+//            first and last MiB of imd.dat, the short-read length threshold
 //   hits     row_ptr u64[N1 + 1], sid i32[H] (sign = strand), pos i32[H], insertL i32[H] (paired-end only)
 //   per read set (un, alignable, max), per mate: off u64[n + 1], base codes u8 (A0 C1 G2 T3 N4), phred values u8
 //   per read set: (index, name) of every read with a mate shorter than kSidecarShortLen (the reference warns about
 //            reads shorter than the seed length by name, SingleQModel.h:296-302)
 //
-// It is used only if every recorded file size still matches the text files next to it; otherwise rsem-run-em parses
+// It is used only if every recorded file size (and the .dat fingerprint) still matches the text files next to it; otherwise rsem-run-em parses
 // the text as before.  Little-endian, no alignment padding (sections are read with fread into their final vectors).
 #include <sys/stat.h>
 
@@ -25,7 +25,7 @@ namespace host {
 namespace {
 
 constexpr char kMagic[8] = {'R', 'S', 'E', 'M', 'B', '2', '0', '0'};
-constexpr uint32_t kVersion = 1;
+constexpr uint32_t kVersion = 2;
 
 struct Header {
     char magic[8];
@@ -34,6 +34,7 @@ struct Header {
     uint64_t dat_bytes;
     uint64_t read_bytes[3][2];
     uint32_t short_len, reserved;
+    uint64_t dat_hash;   // FNV-1a over the first and the last MiB of imd.dat
 };
 
 uint64_t file_bytes(const std::string& path) {
@@ -41,8 +42,26 @@ uint64_t file_bytes(const std::string& path) {
     return stat(path.c_str(), &st) == 0 ? (uint64_t)st.st_size : 0;
 }
 
+// content fingerprint of a text file that is cheap at any size: FNV-1a over its first and last MiB
+uint64_t edge_hash(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return 0;
+    constexpr size_t kEdge = 1u << 20;
+    std::vector<unsigned char> buf(kEdge);
+    uint64_t hsh = 1469598103934665603ull;
+    auto mix = [&](size_t n) { for (size_t i = 0; i < n; ++i) { hsh ^= buf[i]; hsh *= 1099511628211ull; } };
+    mix(fread(buf.data(), 1, kEdge, f));
+    if (fseek(f, 0, SEEK_END) == 0) {
+        const long sz = ftell(f);
+        if (sz > (long)kEdge && fseek(f, sz - (long)kEdge, SEEK_SET) == 0) mix(fread(buf.data(), 1, kEdge, f));
+    }
+    fclose(f);
+    return hsh;
+}
+
 void fill_sizes(const std::string& imd, int read_type, Header& h) {
     h.dat_bytes = file_bytes(imd + ".dat");
+    h.dat_hash = edge_hash(imd + ".dat");
     for (int tag = 0; tag < 3; ++tag) {
         std::vector<std::string> files;
         read_type_files(imd, tag, read_type, files);
@@ -133,7 +152,7 @@ bool load_sidecar(const std::string& imd, int read_type, Sidecar& out) {
     if (ok) {  // does it still describe the text files next to it?
         memset(&now, 0, sizeof now);
         fill_sizes(imd, read_type, now);
-        ok = now.dat_bytes == h.dat_bytes && !memcmp(now.read_bytes, h.read_bytes, sizeof h.read_bytes);
+        ok = now.dat_bytes == h.dat_bytes && now.dat_hash == h.dat_hash && !memcmp(now.read_bytes, h.read_bytes, sizeof h.read_bytes);
     }
     if (!ok) { fclose(fi); return false; }
     const bool paired = read_type >= 2, hasq = read_type & 1;

@@ -181,3 +181,18 @@ def test_sidecar_equals_the_text_files(built, tmp_path, read_type):
     os.makedirs(f"{out2}/t"); os.makedirs(f"{out2}/s")
     subprocess.check_call([OURS, f"{d}/ref/r", f"{out2}/t/s", f"{out2}/s/s", f"{d}/aln.sam", str(read_type), "-q"], env=env)
     assert not os.path.exists(f"{out2}/t/s.b200")
+
+
+def test_sidecar_refused_when_dat_content_changes_at_equal_size(built, tmp_path):
+    d = rf.gen_dataset(str(tmp_path / "d"), read_type=0, M=60, N1=800, N0=50, read_len=40, seed=2, sam=1)
+    out = str(tmp_path / "o")
+    assert _parse(OURS, d, f"{d}/aln.sam", 0, out).returncode == 0
+    imd = f"{out}/t/s"
+    ok = subprocess.run([SELFTEST, "--sidecar", imd, "0", "1", "25", "0", str(tmp_path / "a")], stdout=subprocess.PIPE, text=True)
+    assert ok.returncode == 0
+    data = bytearray(open(imd + ".dat", "rb").read())
+    k = data.rindex(b" ")          # change one digit of the last position: same size, other content
+    data[k + 1] = ord("7") if data[k + 1] != ord("7") else ord("8")
+    open(imd + ".dat", "wb").write(bytes(data))
+    bad = subprocess.run([SELFTEST, "--sidecar", imd, "0", "1", "25", "0", str(tmp_path / "b")], stdout=subprocess.PIPE, text=True)
+    assert bad.returncode == 3 and "no usable side-car" in bad.stdout
