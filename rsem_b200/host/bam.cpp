@@ -78,6 +78,7 @@ struct AlnReader::Source {
     std::mutex mu;
     std::condition_variable cv;
     std::deque<std::vector<uint8_t>> ready;   // decoded batches, in file order
+    std::vector<std::vector<uint8_t>> spare;  // consumed batch buffers, handed back to the producer (no re-allocation, no page faults)
     bool done = false, stop = false;
 
     static bool looks_like_bgzf(const uint8_t* h, size_t n) {
@@ -124,7 +125,12 @@ struct AlnReader::Source {
                 u_total += u_len;
             }
             if (!blks.empty()) {
-                std::vector<uint8_t> out(u_total);
+                std::vector<uint8_t> out;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (!spare.empty()) { out.swap(spare.back()); spare.pop_back(); }
+                }
+                out.resize(u_total);
                 std::atomic<size_t> next(0);
                 std::atomic<int> bad(0);
                 auto work = [&]() {
@@ -181,6 +187,7 @@ struct AlnReader::Source {
             for (;;) {
                 cv.wait(lk, [&]() { return !ready.empty() || done; });
                 if (ready.empty()) { eof = true; return false; }
+                if (buf.capacity()) { spare.emplace_back(); spare.back().swap(buf); }
                 buf = std::move(ready.front());
                 ready.pop_front();
                 cv.notify_all();
