@@ -126,7 +126,9 @@ int rsem_b200_shard_reads(uint64_t N, const uint64_t* row_ptr /* N + 1 */, int32
 int rsem_b200_upload_hits(rsem_b200_ctx* ctx, uint64_t N, uint64_t H, int32_t M, const uint64_t* row_ptr,
                           const int32_t* sid, const int32_t* pos, const int32_t* insertL);
 /* Directly set hit.conprb / ncpv (used when resuming from an .ofg-like matrix, by tests and the
- * benchmark).  conprb: H doubles, ncpv: N doubles.                                              */
+ * benchmark).  conprb: H doubles, ncpv: N doubles.  The copies run on a second stream; meanwhile the
+ * directory of the equivalence-class layout the frozen-conprb rounds use (it depends on row_ptr / sid
+ * only) is built on the device, so a following rsem_b200_em_rounds starts without that latency.    */
 int rsem_b200_upload_conprb(rsem_b200_ctx* ctx, const double* conprb, const double* ncpv);
 int rsem_b200_download_conprb(rsem_b200_ctx* ctx, double* conprb, double* ncpv);
 /* Same as upload_hits + upload_conprb but from DEVICE pointers already resident on ctx's GPU
