@@ -196,3 +196,37 @@ def test_sidecar_refused_when_dat_content_changes_at_equal_size(built, tmp_path)
     open(imd + ".dat", "wb").write(bytes(data))
     bad = subprocess.run([SELFTEST, "--sidecar", imd, "0", "1", "25", "0", str(tmp_path / "b")], stdout=subprocess.PIPE, text=True)
     assert bad.returncode == 3 and "no usable side-car" in bad.stdout
+
+
+def test_reader_variants_give_the_same_files(built, tmp_path):
+    """AlnReader (host/bam.cpp): plain SAM, gzip'ed SAM (one gzip member: zlib's gz layer), BAM = BGZF (blocks inflated on
+    1 or 8 worker threads ahead of the parser) - the same output files every time; a truncated BAM is an error, not a
+    short result."""
+    import gzip
+    d = rf.gen_dataset(str(tmp_path / "d"), read_type=3, M=90, N1=6000, N0=300, read_len=45, seed=4, sam=1, spurious=0.02)
+    sam = f"{d}/aln.sam"
+    gz = str(tmp_path / "aln.sam.gz")
+    with open(sam, "rb") as fi, gzip.open(gz, "wb", compresslevel=1) as fo:
+        fo.write(fi.read())
+    bam = str(tmp_path / "aln.bam")
+    subprocess.check_call([SELFTEST, "--bam-copy", sam, bam, "3"], stdout=subprocess.DEVNULL)
+    assert os.path.getsize(bam) > 10 * 65536 / 8   # several BGZF blocks
+    outs = {}
+    for tag, aln, env in (("sam", sam, {}), ("gz", gz, {}), ("bam1", bam, {"RSEM_B200_IO_THREADS": "1"}),
+                          ("bam8", bam, {"RSEM_B200_IO_THREADS": "8"})):
+        out = str(tmp_path / tag)
+        os.makedirs(f"{out}/t"); os.makedirs(f"{out}/s")
+        p = subprocess.run([OURS, f"{d}/ref/r", f"{out}/t/s", f"{out}/s/s", aln, "3", "-q"], env=dict(os.environ, **env),
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 0, p.stderr
+        outs[tag] = out
+    for tag in ("gz", "bam1", "bam8"):
+        _assert_same_tree(outs["sam"], outs[tag])
+        assert open(outs[tag] + "/t/s.b200", "rb").read() == open(outs["sam"] + "/t/s.b200", "rb").read()
+    # truncated in the middle of a block
+    cut = str(tmp_path / "cut.bam")
+    open(cut, "wb").write(open(bam, "rb").read()[: os.path.getsize(bam) // 2])
+    out = str(tmp_path / "cut")
+    os.makedirs(f"{out}/t"); os.makedirs(f"{out}/s")
+    p = subprocess.run([OURS, f"{d}/ref/r", f"{out}/t/s", f"{out}/s/s", cut, "3", "-q"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 255 and ("Truncated" in p.stderr or "Corrupt" in p.stderr or "corrupt" in p.stderr)
