@@ -10,12 +10,12 @@
 //   * MT19937 is regenerated 624 words at a time by the chain's warp (three dependent phases of the
 //     standard recurrence), tempering is done at extraction.
 //
-// Mapping (round 1): one CTA per chain (chains are the reference's "threads" and never interact),
-// warp 0 walks the reads in order - the loads, the (count + alpha) * conprb products and the
-// index count are spread over its 32 lanes, only the running sum is serial - and the whole CTA
-// does the O(M) per-sample work (count vector dump, theta -> polish -> TPM/FPKM, accumulation).
-// The within-chain dependence (every draw reads counts written by the previous reads) makes this
-// latency-bound; the component-parallel exact scheme of SURVEY.md A.4 is the planned next step.
+// Two kernels: gibbs_chain_kernel (serial cross-check: one CTA per chain, warp 0 walks the reads in order - the loads,
+// the (count + alpha) * conprb products and the index count are spread over its 32 lanes, only the running sum is
+// serial) and gibbs_parallel_kernel (the product path: connected components of the read x transcript graph walked
+// concurrently by 16-lane groups, exact through a fixed-point iteration over the reads that change their noise
+// membership; see the block comment "Component-parallel EXACT sampler" below).  In both, the chain's CTA(s) also do the
+// O(M) per-sample work (count vector dump, theta -> polish -> TPM/FPKM, accumulation).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(kGibbsThreads) gibbs_chain_kernel(const GibbsA
 //
 //   * Static, once per upload (gibbs_prepare, host): connected components (union-find over transcripts); the reads
 //     grouped by component in read order ("segments", longest first); rows re-laid in that slot order.
-//   * A sweep of a chain: every segment is walked by ONE thread in read order with the live counts of its component
-//     (component-private, plain loads / stores).  The noise count read i must see is c0(i) = c0 at the start of the
+//   * A sweep of a chain: every segment is walked by ONE group of 16 lanes in read order with the live counts of its
+//     component (component-private: registers for components of < 32 transcripts, L2 otherwise).  The noise count read i must see is c0(i) = c0 at the start of the
 //     sweep + (#reads before i that joined the noise transcript) - (#reads before i that left it).  Those "flips" are
 //     rare, so the sweep is a fixed-point iteration over the SET of flips:
 //         pass k walks all segments with c0(i) taken from the flips recorded by pass k - 1 (none for k = 0) and
@@ -1377,7 +1377,7 @@ static int gibbs_run_parallel(rsem_b200_ctx* c, const rsem_b200_gibbs_params* p,
     a.n0 = p->n0; a.totc = p->totc;
     a.n_words = W;
 
-    // co-resident CTAs: chains run in waves, every chain gets the same number of worker CTAs (one thread per component
+    // co-resident CTAs: chains run in waves, every chain gets the same number of worker CTAs (one lane group per component
     // is all the parallelism a sweep has) + 1 generator CTA
     // RSEM_B200_GIBBS_PF: 2 (default) pipelined walk with both lane groups of a warp in one loop, 1 pipelined walk per
     // segment, 0 row-at-a-time walk (prefetch distance 1); 0 and 1 are kept as cross-checks
