@@ -506,7 +506,7 @@ def run_ours(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 times = [float(x) for x in t.tolist()]
             assert abs(th.sum() - 1.0) < 1e-9
-            dt = sorted(times)[len(times) // 2]   # median job: single uploads are sometimes 3-4x slower (host side), see profiles/README.md
+            dt = sorted(times)[len(times) // 2]   # median job: about one upload_hits in four takes 3-5x longer (cause not identified), see profiles/README.md
             res[rounds] = (total_hits * rounds / dt, dt, [round(x, 4) for x in times])
         r0 = E2E_ROUNDS[0]
         e2e = {"value": res[r0][0], "unit": "hits/s", "h2d_bytes_per_step": bytes_in // r0, "d2h_bytes_per_step": bytes_out // r0,
