@@ -219,8 +219,8 @@ bool load_allele_groups(const std::string& ref_name, std::vector<int>& gt, std::
 void load_mparams(const std::string& path, ModelParamsH& p) {
     std::vector<char> buf = slurp(path);
     Cursor c(buf);
-    long long v;
-    double d;
+    long long v = 0;
+    double d = 0.0;
     bool ok = c.next_i64(v); p.minL = (int)v;
     ok = ok && c.next_i64(v); p.maxL = (int)v;
     ok = ok && c.next_f64(d); p.probF = d;
