@@ -261,6 +261,25 @@ struct AlnReader::Source {
     }
 };
 
+// SAM text -> records on worker threads (conv_run / conv_next below)
+struct AlnReader::Conv {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::vector<uint8_t>> ready;
+    std::vector<std::vector<uint8_t>> spare;
+    bool done = false, stop = false;
+    std::vector<uint8_t> cur;   // consumer side
+    size_t at = 0;
+    ~Conv() {
+        if (th.joinable()) {
+            { std::lock_guard<std::mutex> lk(mu); stop = true; }
+            cv.notify_all();
+            th.join();
+        }
+    }
+};
+
 AlnReader::AlnReader(const std::string& path) : src_(new Source) {
     FILE* probe = fopen(path.c_str(), "rb");
     if (!probe) die("Cannot open " + path + "! It may not exist.");
@@ -330,9 +349,16 @@ AlnReader::AlnReader(const std::string& path) : src_(new Source) {
         }
     }
     for (size_t i = 0; i < ref_names_.size(); ++i) ref_index_[ref_names_[i]] = (int)i;
+    if (!is_bam_) {
+        conv_ = new Conv;
+        conv_->th = std::thread([this]() { conv_run(); });
+    }
 }
 
-AlnReader::~AlnReader() { delete src_; }
+AlnReader::~AlnReader() {
+    delete conv_;   // joins the converter, which uses src_
+    delete src_;
+}
 
 bool AlnReader::next(BamRecord& rec) {
     if (is_bam_) {
@@ -344,23 +370,121 @@ bool AlnReader::next(BamRecord& rec) {
         if (!src_->read(rec.data.data(), block)) die("Truncated BAM file!");
         return true;
     }
-    if (have_pending_) {
-        have_pending_ = false;
-        parse_sam_line(pending_.data(), pending_.size(), rec);
-        return true;
+    return conv_next(rec);
+}
+
+// ---- SAM text -> records, pipelined -------------------------------------------------------------------------------------
+// A converter thread takes the text behind the header in chunks of ~16 MB that end at a line boundary, has g_io_threads
+// workers turn the lines of a chunk into BAM-encoded records (u32 size + bytes, the BAM stream format) in parallel and queues
+// the result in file order; next() only frames records out of those buffers.  The reference parses SAM text on one thread.
+void AlnReader::conv_run() {
+    Conv& c = *conv_;
+    constexpr size_t kChunk = 16u << 20;
+    std::string text;
+    if (have_pending_) { text = pending_; text += '\n'; have_pending_ = false; }
+    bool input_end = false;
+    std::vector<std::vector<uint8_t>> part;
+    while (!input_end || !text.empty()) {
+        // fill up to kChunk from the source (this thread is the only user of src_ from here on)
+        while (!input_end && text.size() < kChunk) {
+            if (src_->at == src_->end && !src_->fill()) { input_end = true; break; }
+            text.append(reinterpret_cast<const char*>(src_->buf.data() + src_->at), src_->end - src_->at);
+            src_->at = src_->end;
+        }
+        size_t use = text.size();
+        if (!input_end) {
+            const size_t nl = text.rfind('\n');
+            if (nl == std::string::npos) continue;   // a single line longer than the chunk: keep reading
+            use = nl + 1;
+        }
+        if (use == 0) break;
+        // line-aligned ranges for the workers
+        const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, g_io_threads), use / (256u << 10) + 1));
+        std::vector<size_t> cut((size_t)T + 1, use);
+        cut[0] = 0;
+        for (int t = 1; t < T; ++t) {
+            size_t p = use * (size_t)t / (size_t)T;
+            const size_t nl = text.find('\n', p);
+            cut[(size_t)t] = (nl == std::string::npos || nl + 1 > use) ? use : nl + 1;
+        }
+        part.resize((size_t)T);
+        auto work = [&](int t) {
+            std::vector<uint8_t>& out = part[(size_t)t];
+            out.clear();
+            BamRecord rec;
+            int last_ref = -1;
+            const char* p = text.data() + cut[(size_t)t];
+            const char* e = text.data() + cut[(size_t)t + 1];
+            while (p < e) {
+                const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(e - p)));
+                const char* le = nl ? nl : e;
+                size_t n = (size_t)(le - p);
+                if (n && p[n - 1] == '\r') --n;
+                if (n) {
+                    parse_sam_line(p, n, rec, last_ref);
+                    const uint32_t sz = (uint32_t)rec.data.size();
+                    const size_t at = out.size();
+                    out.resize(at + 4 + sz);
+                    wr_u32(out.data() + at, sz);
+                    memcpy(out.data() + at + 4, rec.data.data(), sz);
+                }
+                p = nl ? nl + 1 : e;
+            }
+        };
+        if (T == 1) work(0);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < T; ++t) pool.emplace_back(work, t);
+            for (auto& th : pool) th.join();
+        }
+        size_t total = 0;
+        for (int t = 0; t < T; ++t) total += part[(size_t)t].size();
+        std::vector<uint8_t> out;
+        {
+            std::lock_guard<std::mutex> lk(c.mu);
+            if (!c.spare.empty()) { out.swap(c.spare.back()); c.spare.pop_back(); }
+        }
+        out.resize(total);
+        size_t at = 0;
+        for (int t = 0; t < T; ++t) {
+            if (!part[(size_t)t].empty()) memcpy(out.data() + at, part[(size_t)t].data(), part[(size_t)t].size());
+            at += part[(size_t)t].size();
+        }
+        text.erase(0, use);
+        if (total) {
+            std::unique_lock<std::mutex> lk(c.mu);
+            c.cv.wait(lk, [&]() { return c.ready.size() < 3 || c.stop; });
+            if (c.stop) return;
+            c.ready.push_back(std::move(out));
+            c.cv.notify_all();
+        }
     }
-    const char* p;
-    size_t n;
-    do {
-        if (!src_->line_view(p, n, spill_)) return false;
-    } while (n == 0);
-    parse_sam_line(p, n, rec);
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.done = true;
+    c.cv.notify_all();
+}
+
+bool AlnReader::conv_next(BamRecord& rec) {
+    Conv& c = *conv_;
+    if (c.at == c.cur.size()) {
+        std::unique_lock<std::mutex> lk(c.mu);
+        c.cv.wait(lk, [&]() { return !c.ready.empty() || c.done; });
+        if (c.ready.empty()) return false;
+        if (c.cur.capacity()) { c.spare.emplace_back(); c.spare.back().swap(c.cur); }
+        c.cur = std::move(c.ready.front());
+        c.ready.pop_front();
+        c.at = 0;
+        c.cv.notify_all();
+    }
+    const uint32_t sz = rd_u32(c.cur.data() + c.at);
+    rec.data.assign(c.cur.data() + c.at + 4, c.cur.data() + c.at + 4 + sz);
+    c.at += 4 + (size_t)sz;
     return true;
 }
 
 // SAM text -> BAM record (SAM spec section 4.2; field encodings as htslib's sam_parse1 chooses them).  No allocation per
 // line: fields are (pointer, length) views into the reader's buffer, the record's byte vector is reused by the caller.
-void AlnReader::parse_sam_line(const char* ln, size_t len, BamRecord& rec) const {
+void AlnReader::parse_sam_line(const char* ln, size_t len, BamRecord& rec, int& last_ref_) const {
     struct Fld { const char* p; size_t n; };
     Fld f[11];
     const char* end = ln + len;

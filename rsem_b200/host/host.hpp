@@ -216,15 +216,19 @@ public:
 
 private:
     struct Source;
+    struct Conv;          // SAM text -> BAM records on worker threads, ahead of next()
     Source* src_;
+    Conv* conv_ = nullptr;
     bool is_bam_ = false, have_pending_ = false;
     std::string text_, pending_;
     std::vector<std::string> ref_names_;
     std::vector<uint32_t> ref_lens_;
     std::map<std::string, int> ref_index_;
-    mutable int last_ref_ = -1;   // RNAME of the previous line (alignments of a read mostly share it or repeat it)
     std::string spill_;           // a line that crosses a buffer boundary
-    void parse_sam_line(const char* ln, size_t len, BamRecord& rec) const;
+    // last_ref: RNAME of the caller's previous line (alignments of a read mostly share it or repeat it)
+    void parse_sam_line(const char* ln, size_t len, BamRecord& rec, int& last_ref) const;
+    void conv_run();
+    bool conv_next(BamRecord& rec);
 };
 
 std::string rsem_bam_header_text(const std::string& in_text);  // SamHeader(text) + insertPG("RSEM")

@@ -15,7 +15,10 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <map>
+#include <mutex>
 #include <thread>
 
 #include "host.hpp"
@@ -24,19 +27,85 @@ using namespace host;
 
 namespace {
 
-struct OutFile {   // buffered text output; removed at the end if its category stayed empty (parseIt.cpp:158-170)
+// Text output: every file appends to a 4 MB buffer; full buffers go to ONE background writer thread (FIFO, so the order per
+// file is kept), which keeps the write syscalls off the parsing thread.  Files of categories that stayed empty are removed at
+// the end (parseIt.cpp:158-170).
+class Writer {
+public:
+    Writer() : th_([this]() { run(); }) {}
+    ~Writer() { finish(); }
+    void submit(FILE* f, const std::string* path, std::string&& data) {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&]() { return q_.size() < 16; });
+        q_.push_back(Job{f, path, std::move(data)});
+        cv_.notify_all();
+    }
+    std::string spare() {   // an emptied buffer with its capacity, if one is available
+        std::lock_guard<std::mutex> lk(mu_);
+        if (spare_.empty()) return std::string();
+        std::string s = std::move(spare_.back());
+        spare_.pop_back();
+        return s;
+    }
+    void drain() {   // everything submitted so far is on its way to the kernel
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&]() { return q_.empty() && !busy_; });
+    }
+    void finish() {
+        if (!th_.joinable()) return;
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        th_.join();
+    }
+
+private:
+    struct Job { FILE* f; const std::string* path; std::string data; };
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Job> q_;
+    std::vector<std::string> spare_;
+    bool stop_ = false, busy_ = false;
+    std::thread th_;
+    void run() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&]() { return !q_.empty() || stop_; });
+                if (q_.empty()) return;
+                j = std::move(q_.front());
+                q_.pop_front();
+                busy_ = true;
+                cv_.notify_all();
+            }
+            if (fwrite(j.data.data(), 1, j.data.size(), j.f) != j.data.size()) die("Cannot write " + *j.path + " (disk full?)!");
+            j.data.clear();
+            std::lock_guard<std::mutex> lk(mu_);
+            if (spare_.size() < 8) spare_.push_back(std::move(j.data));
+            busy_ = false;
+            cv_.notify_all();
+        }
+    }
+};
+
+struct OutFile {
     std::string path;
     FILE* f = nullptr;
     std::string buf;
-    void open(const std::string& p) {
+    Writer* w = nullptr;
+    void open(const std::string& p, Writer* writer) {
         path = p;
+        w = writer;
         f = fopen(p.c_str(), "w");
         if (!f) die("Cannot open " + p + " for writing!");
         buf.reserve(1 << 22);
     }
     void flush() {
-        if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) die("Cannot write " + path + " (disk full?)!");
+        if (buf.empty()) return;
+        w->submit(f, &path, std::move(buf));
+        buf = w->spare();
         buf.clear();
+        if (buf.capacity() < (1u << 22)) buf.reserve(1 << 22);
     }
     void put(const char* p, size_t n) {
         buf.append(p, n);
@@ -44,8 +113,7 @@ struct OutFile {   // buffered text output; removed at the end if its category s
     }
     void put(const std::string& s) { put(s.data(), s.size()); }
     void put(char c) { buf.push_back(c); }
-    void close() {
-        flush();
+    void close() {   // after Writer::drain()
         if (fclose(f) != 0) die("Cannot write " + path + " (disk full?)!");
         f = nullptr;
     }
@@ -298,14 +366,15 @@ int main(int argc, char* argv[]) {
         fclose(fo);
     }
 
+    Writer writer;
     OutFile cat[3][2];
     for (int t = 0; t < 3; ++t) {
         std::vector<std::string> files;
         read_type_files(imdName, t, read_type, files);
-        for (int m = 0; m < n_os; ++m) cat[t][m].open(files[(size_t)m]);
+        for (int m = 0; m < n_os; ++m) cat[t][m].open(files[(size_t)m], &writer);
     }
     OutFile dat;
-    dat.open(imdName + ".dat");
+    dat.open(imdName + ".dat", &writer);
     dat.put(std::string(99, ' '));   // room for the header, filled in at the end (parseIt.cpp:197-199, 208-209)
     dat.put('\n');
 
@@ -380,6 +449,8 @@ int main(int argc, char* argv[]) {
     const uint64_t nUnique = N[1] - nMulti;
 
     dat.flush();
+    for (int t = 0; t < 3; ++t) for (int m = 0; m < n_os; ++m) cat[t][m].flush();
+    writer.drain();
     {   // the header over the reserved blanks
         const int n = snprintf(tmp, sizeof tmp, "%llu %llu %d", (unsigned long long)N[1], (unsigned long long)nHits, read_type);
         if (fseek(dat.f, 0, SEEK_SET) != 0 || fwrite(tmp, 1, (size_t)n, dat.f) != (size_t)n) die("Cannot write " + dat.path + "!");
