@@ -574,14 +574,16 @@ void AlnReader::parse_sam_line(const char* ln, size_t len, BamRecord& rec, int& 
     w += qname.n;
     *w++ = 0;
     for (size_t i = 0; i < n_cig; ++i) { wr_u32(w, cg[i]); w += 4; }
-    static uint8_t nt16[256];
-    static bool nt_init = false;
-    if (!nt_init) {
-        memset(nt16, 15, sizeof nt16);
-        const char* code = "=ACMGRSVTWYHKDBN";
-        for (int i = 0; i < 16; ++i) { nt16[(uint8_t)code[i]] = (uint8_t)i; nt16[(uint8_t)tolower(code[i])] = (uint8_t)i; }
-        nt_init = true;
-    }
+    struct Nt16 {   // letter -> 4-bit code; built once (thread-safe static initialisation: worker threads call this function)
+        uint8_t v[256];
+        Nt16() {
+            memset(v, 15, sizeof v);
+            const char* code = "=ACMGRSVTWYHKDBN";
+            for (int i = 0; i < 16; ++i) { v[(uint8_t)code[i]] = (uint8_t)i; v[(uint8_t)tolower(code[i])] = (uint8_t)i; }
+        }
+    };
+    static const Nt16 nt16_table;
+    const uint8_t* nt16 = nt16_table.v;
     for (int i = 0; i < l_seq; i += 2) {
         const uint8_t hi = nt16[(uint8_t)seq.p[i]], lo = i + 1 < l_seq ? nt16[(uint8_t)seq.p[i + 1]] : 0;
         *w++ = (uint8_t)(hi << 4 | lo);
