@@ -230,3 +230,22 @@ def test_reader_variants_give_the_same_files(built, tmp_path):
     os.makedirs(f"{out}/t"); os.makedirs(f"{out}/s")
     p = subprocess.run([OURS, f"{d}/ref/r", f"{out}/t/s", f"{out}/s/s", cut, "3", "-q"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert p.returncode == 255 and ("Truncated" in p.stderr or "Corrupt" in p.stderr or "corrupt" in p.stderr)
+
+
+@pytest.mark.parametrize("name,read_type,extra", [("parse_pe_q", 3, ()), ("parse_se_noq_tag", 0, ("-tag", "XM"))])
+def test_golden_outputs_of_the_reference(built, tmp_path, name, read_type, extra):
+    """tests/golden/parse_*.tar.gz (tools/make_golden_parse.py): outputs of the reference's own rsem-parse-alignments; pins our
+    program where oracle/_ref is not available.  SAM input and the BAM made from it."""
+    import tarfile
+    with tarfile.open(os.path.join(ROOT, "tests", "golden", name + ".tar.gz")) as tar:
+        tar.extractall(tmp_path, filter="data")
+    g = str(tmp_path / name)
+    bam = str(tmp_path / "aln.bam")
+    subprocess.check_call([SELFTEST, "--bam-copy", f"{g}/aln.sam", bam, "2"], stdout=subprocess.DEVNULL)
+    for tag, aln in (("sam", f"{g}/aln.sam"), ("bam", bam)):
+        out = str(tmp_path / tag)
+        os.makedirs(f"{out}/t"); os.makedirs(f"{out}/s")
+        p = subprocess.run([OURS, f"{g}/ref/r", f"{out}/t/s", f"{out}/s/s", aln, str(read_type), "-q", *extra],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 0, p.stderr
+        _assert_same_tree(f"{g}/out", out)
