@@ -3,7 +3,7 @@
 # writer thread) on a generated SAM file and the BAM made from it.  CPU only.  Usage: tools/sanitize_host.sh [workdir]
 set -e
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
-W="${1:-$(mktemp -d)}"
+W="${1:-$(mktemp -d)}"; mkdir -p "$W"
 SRC="$ROOT/rsem_b200/host/main_parse.cpp $ROOT/rsem_b200/host/bam.cpp $ROOT/rsem_b200/host/files.cpp $ROOT/rsem_b200/host/model.cpp $ROOT/rsem_b200/host/results.cpp $ROOT/rsem_b200/host/sidecar.cpp"
 LINK="-I$ROOT/include -L$ROOT/rsem_b200 -lrsem_b200 -Wl,-rpath,$ROOT/rsem_b200 -lz -pthread"
 g++ -O1 -g -fsanitize=thread -std=c++17 -o "$W/parse_tsan" $SRC $LINK
