@@ -536,8 +536,10 @@ static bool load_ofg_sidecar(const std::string& path, int M, uint64_t& N0, std::
     FILE* fb = fopen((path + ".b200").c_str(), "rb");
     if (!fb) return false;
     OfgHeader hd;
+    const uint64_t have = file_size_of(path + ".b200");
     bool ok = fread(&hd, sizeof hd, 1, fb) == 1 && !memcmp(hd.magic, kOfgMagic, 8) && hd.M == (uint64_t)M &&
-              hd.ofg_bytes == file_size_of(path) && hd.ofg_bytes > 0;
+              hd.ofg_bytes == file_size_of(path) && hd.ofg_bytes > 0 && hd.entries <= have / 12 && hd.rows <= have / 8 &&
+              have == sizeof hd + 8 * (hd.rows + 1) + 12 * hd.entries;
     if (ok) {
         row_ptr.resize((size_t)hd.rows + 1);
         sid.resize((size_t)hd.entries);

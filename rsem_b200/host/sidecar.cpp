@@ -154,6 +154,11 @@ bool load_sidecar(const std::string& imd, int read_type, Sidecar& out) {
         fill_sizes(imd, read_type, now);
         ok = now.dat_bytes == h.dat_bytes && now.dat_hash == h.dat_hash && !memcmp(now.read_bytes, h.read_bytes, sizeof h.read_bytes);
     }
+    if (ok) {   // the counts of a damaged header must not size the allocations below: the hit sections alone need this much
+        const uint64_t have = file_bytes(path);
+        const uint64_t per_hit = read_type >= 2 ? 12 : 8;
+        ok = h.H <= have / per_hit && h.N[1] <= have / 8 && h.N[0] <= have / 8 && h.N[2] <= have / 8;
+    }
     if (!ok) { fclose(fi); return false; }
     const bool paired = read_type >= 2, hasq = read_type & 1;
     out = Sidecar();
@@ -172,7 +177,7 @@ bool load_sidecar(const std::string& imd, int read_type, Sidecar& out) {
             ok = get_vec(fi, rs.off[m], (size_t)rs.n + 1);
             if (!ok) break;
             const size_t nb = rs.n ? (size_t)rs.off[m][rs.n] : 0;
-            ok = get_vec(fi, rs.base[m], nb) && (!hasq || get_vec(fi, rs.qual[m], nb));
+            ok = nb <= file_bytes(path) && get_vec(fi, rs.base[m], nb) && (!hasq || get_vec(fi, rs.qual[m], nb));
         }
         uint64_t ns = 0;
         ok = ok && fread(&ns, 8, 1, fi) == 1 && ns <= rs.n;

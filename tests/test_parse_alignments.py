@@ -249,3 +249,20 @@ def test_golden_outputs_of_the_reference(built, tmp_path, name, read_type, extra
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert p.returncode == 0, p.stderr
         _assert_same_tree(f"{g}/out", out)
+
+
+def test_damaged_sidecar_is_refused_not_trusted(built, tmp_path):
+    d = rf.gen_dataset(str(tmp_path / "d"), read_type=1, M=60, N1=900, N0=60, read_len=40, seed=6, sam=1)
+    out = str(tmp_path / "o")
+    assert _parse(OURS, d, f"{d}/aln.sam", 1, out).returncode == 0
+    imd = f"{out}/t/s"
+    blob = bytearray(open(imd + ".b200", "rb").read())
+    import struct
+    for what, patch in (("huge H", lambda b: b.__setitem__(slice(40, 48), struct.pack("<Q", 1 << 60))),
+                        ("truncated", lambda b: b.__delitem__(slice(len(b) // 2, len(b))))):
+        bad = bytearray(blob)
+        patch(bad)
+        open(imd + ".b200", "wb").write(bytes(bad))
+        p = subprocess.run([SELFTEST, "--sidecar", imd, "1", "1", "25", "0", str(tmp_path / "x")], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 3 and "no usable side-car" in p.stdout, what
